@@ -1,0 +1,109 @@
+"""CPU: the oracle (torch port + float64 closed form) against the frozen reference outputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form as cf
+from oracle import ref_port as port
+from tests.common import CFG0, CFG2, FULL_CASES, STATS_CASES, Golden, assert_close, to_np
+
+
+def _grads(fn, leaves):
+    out = fn()
+    out['residual'].mean().backward()
+    return out, [None if l is None else l.grad for l in leaves]
+
+
+@pytest.mark.parametrize("case", FULL_CASES)
+def test_port_reproduces_reference(case):
+    g = Golden(case)
+    for lvl in range(g.n_levels):
+        tag = f"L{lvl}_"
+        k = g.k().requires_grad_(True)
+        pose = g.poses()[0].clone().requires_grad_(True)
+        aff = g.affine(0)
+        if aff is not None:
+            aff = tuple(a.clone().requires_grad_(True) for a in aff)
+        out, gr = _grads(lambda: port.cost_single(g.src(lvl), g.trg(lvl), k, pose, CFG0, aff), [k, pose])
+        assert_close(to_np(out['residual']), g.z[tag + "single_residual"], 1e-6, "residual")
+        assert_close(to_np(gr[0]), g.z[tag + "single_g_k"], 1e-5, "g_k")
+        assert_close(to_np(gr[1]), g.z[tag + "single_g_pose"], 1e-5, "g_pose")
+        # batch
+        k = g.k().requires_grad_(True)
+        poses = g.poses().clone().requires_grad_(True)
+        aff = g.affine()
+        out = port.cost_batch(g.src(lvl), g.trg_images(lvl), g.trg_Ks(), k, poses, CFG0, aff)
+        out['residual'].mean().backward()
+        assert_close(to_np(out['residual']), g.z[tag + "batch_residual"], 1e-6, "batch residual")
+        assert_close(to_np(k.grad), g.z[tag + "batch_g_k"], 1e-5, "batch g_k")
+        assert_close(to_np(poses.grad), g.z[tag + "batch_g_poses"], 1e-5, "batch g_poses")
+
+
+@pytest.mark.parametrize("case", STATS_CASES)
+def test_port_stats_and_geometry(case):
+    g = Golden(case)
+    lvl = g.n_levels - 1
+    out = port.cost_single(g.src(lvl), g.trg(lvl), g.k(), g.poses()[0], CFG2, g.affine(0))
+    for key in ['segm_ids', 'src_valid_mask', 'trg_valid_mask', 'full_mask']:
+        assert np.array_equal(to_np(out[key]), g.z[f"L{lvl}_single_{key}"]), key
+    for key in ['src_pts', 'src_in_trg_pts', 'residual_raw', 'src_in_trg_pixels', 'src_in_trg_keypoints']:
+        assert_close(to_np(out[key]), g.z[f"L{lvl}_single_{key}"], 1e-6, key)
+    with torch.no_grad():
+        assert_close(to_np(port.dense_depths(g.src(lvl), g.k())), g.z["dense_depths"], 1e-6, "dense")
+        for tag, pose, mean in [("render_id", None, False), ("render_pose", g.poses()[0], False),
+                                ("render_mean", g.poses()[0], True)]:
+            assert_close(to_np(port.render_keyframe_depth(g.src(lvl), g.k(), pose, mean)), g.z[tag], 1e-6, tag)
+        est = g.t("reinit_est_depth")
+        for mode in ("median", "mean"):
+            kk, vis = port.segment_median_reinit(est, g.src(lvl), mode)
+            assert_close(to_np(kk), g.z[f"reinit_{mode}"], 1e-6, mode)
+            assert np.array_equal(to_np(vis), g.z["reinit_visible"])
+
+
+@pytest.mark.parametrize("case", FULL_CASES)
+@pytest.mark.parametrize("batch", [False, True])
+def test_closed_form_matches_reference(case, batch):
+    """float64 analytic cost + gradients vs the reference's float32 autograd."""
+    g = Golden(case)
+    geo = cf.compact_geometry(g.z["src_regions"], g.z["src_logdepth"], g.z["src_keypoints"])
+    for lvl in range(g.n_levels):
+        tag = f"L{lvl}_"
+        simg = g.z[tag + "src_image"]
+        timgs = g.z[tag + "trg_images"]
+        js = range(g.B) if batch else [0]
+        costs, gk = [], 0.0
+        for j in js:
+            aff = None
+            if g.with_affine:
+                aff = (g.z["aff_src"], g.z["aff_trg"][j])
+            r = cf.evaluate(geo, simg, timgs[j], g.z["src_K"], g.z["src_K"], g.z["k"], g.z["poses"][j],
+                            aff, batch_thresholds=batch)
+            costs.append(r["cost"])
+            scale = 1.0 / len(list(js))
+            gk = gk + r["g_k"] * scale
+            ref_gp = g.z[tag + ("batch_g_poses" if batch else "single_g_pose")]
+            ref_gp = ref_gp[j] if batch else ref_gp
+            assert_close(r["g_pose"] * scale, ref_gp, 2e-4, f"g_pose[{j}]")
+            if g.with_affine:
+                ref_at = g.z[tag + ("batch_g_aff_trg" if batch else "single_g_aff_trg")]
+                ref_at = ref_at[j] if batch else ref_at
+                assert_close(r["g_aff_trg"] * scale, ref_at, 2e-4, "g_aff_trg")
+        assert_close(np.array(costs), g.z[tag + ("batch_residual" if batch else "single_residual")], 2e-5, "cost")
+        assert_close(gk, g.z[tag + ("batch_g_k" if batch else "single_g_k")], 2e-4, "g_k")
+
+
+def test_closed_form_gn_blocks_are_consistent():
+    """J^T W r from the GN blocks must equal the analytic L1 gradient when W = 1/|r| (IRLS),
+    up to the 1/(3P) normalisation -- ties the (unpinned) GN extension to the pinned gradient."""
+    g = Golden("tiny_rects")
+    geo = cf.compact_geometry(g.z["src_regions"], g.z["src_logdepth"], g.z["src_keypoints"])
+    lvl = g.n_levels - 1
+    r = cf.evaluate(geo, g.z[f"L{lvl}_src_image"], g.z[f"L{lvl}_trg_images"][0], g.z["src_K"], g.z["src_K"],
+                    g.z["k"], g.z["poses"][0], None, want_gn=True, irls_eps=1e-12)
+    P3 = 3.0 * r["P"]
+    assert_close(r["g_d"] / P3, r["g_k"], 1e-9, "depth block")
+    # pose block is in the left tangent: g_tau = sum gY ; g_phi = sum Y x gY
+    gp = r["g_pose"]
+    assert_close(r["g_p"][:3] / P3, gp[:3, 3], 1e-9, "translation block")
+    xi, dk = cf.lm_step(r["A"], r["B"], r["D"], r["g_p"], r["g_d"], 1e-3)
+    assert np.all(np.isfinite(xi)) and np.all(np.isfinite(dk))
