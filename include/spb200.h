@@ -1,0 +1,196 @@
+/*
+ * spb200 -- C ABI of the B200-native dense photometric alignment path.
+ *
+ * This is the drop-in boundary.  The reference
+ * (makezur/super_primitive) is pure Python/PyTorch and has no FFI of its own; the functions
+ * below are what a ctypes binding behind `core.dense_optim`, `core.dense_optim_batch` and
+ * `core.depth_render` calls.  Each entry point cites the reference code
+ * it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C: raw device pointers + sizes, `void* stream` is a cudaStream_t; no torch types.
+ *   - every function returns 0 on success, a negative SPB_E* code on bad arguments, or a positive
+ *     cudaError_t from the launch; nothing here synchronises the stream unless stated.
+ *   - no global state, no context creation at load time (safe under fork-then-init).
+ *   - all arithmetic is float32 (reference dtype); indices are int32.
+ *   - small per-call parameters (K, poses, log-depth seeds, affine terms) are DEVICE pointers so a
+ *     call never forces a device->host sync.
+ */
+#ifndef SPB200_H
+#define SPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPB_OK 0
+#define SPB_EINVAL (-1)
+#define SPB_ELIMIT (-2)
+
+#define SPB_TILE 128          /* points per warp-tile (one segment per tile)            */
+#define SPB_PAD 4             /* every segment's point range is padded to this multiple  */
+#define SPB_PAIR_NOUT 16      /* floats per pair, gradient mode (layout below)           */
+#define SPB_GN_NPOSE 8        /* pose-block columns: 6 twist + 2 target affine           */
+#define SPB_GN_NA 36          /* upper triangle of the 8x8 pose block                    */
+#define SPB_GN_PAIR_NOUT 48   /* 36 A + 8 g_p + cost + wcost + n_valid + pad            */
+#define SPB_GN_SEG_NOUT 10    /* per segment: 8 B-column + D + g_d                       */
+
+/* gradient-mode per-pair output, SPB_PAIR_NOUT floats:
+ *   [0] cost = mean |r| over 3P   [1..3] d/dt   [4..12] d/dR row-major   [13] d/da_trg
+ *   [14] d/db_trg   [15] number of points valid in both views
+ * (source-affine gradients are the negatives of [13],[14]; reference core/dense_optim.py:202-225) */
+
+/* ---- compact source geometry (one keyframe), all pointers on the device -------------------- */
+typedef struct SpbGeom {
+    const uint32_t* uv;        /* [n_pad] u | v<<16 | src_ok<<31   (u = column, v = row)              */
+    const float*    logd;      /* [n_pad] raw per-segment log-depth L[b,v,u]                          */
+    const int32_t*  tiles;     /* [n_tiles][4] {segment, padded start, count, unpadded start}         */
+    const int32_t*  seg_tile;  /* [n_seg+1] CSR: tiles of segment b are [seg_tile[b], seg_tile[b+1])   */
+    const float*    seg_lkp;   /* [n_seg] L[b, kp_row, kp_col]                                         */
+    const float*    K;         /* [9] row-major intrinsics of the geometry grid                       */
+    int32_t n_pts, n_pad, n_seg, n_tiles;
+    int32_t H, W;              /* geometry grid                                                        */
+} SpbGeom;
+
+/* ---- one (source geometry, target image) pair ------------------------------------------------ */
+typedef struct SpbPair {
+    const float* trg_rgba;     /* [Hl][Wl][4] target level image, RGBA-interleaved float32            */
+    const float* src_rgb;      /* [3][n_pad] cached source samples at this level (planar)             */
+    const float* K_trg;        /* [9] target intrinsics (geometry-level K of the target frame)        */
+    const float* pose;         /* [16] row-major 4x4 (source -> target)                               */
+    const float* k;            /* [n_seg] log-depth seeds of the source segments                      */
+    const float* aff_src;      /* [2] (a,b) or NULL                                                   */
+    const float* aff_trg;      /* [2] (a,b) or NULL (both or neither)                                 */
+    int32_t geom;              /* index into the geometry array                                       */
+    int32_t Hl, Wl;            /* level image size                                                    */
+    float   tau;               /* front-of-camera threshold: 1e-7 single, 1e-6 batch                  */
+} SpbPair;
+
+/* optional per-point outputs (collect_stats > 0); any pointer may be NULL.  Indexed by the
+ * UNPADDED point index p (torch.where order), pair j, n = geom.n_pts                              */
+typedef struct SpbStats {
+    float*   src_pts;          /* [n][3]                                                              */
+    float*   moved_pts;        /* [B][n][3]                                                           */
+    float*   trg_px;           /* [B][3][n]  after affine compensation                                */
+    float*   residual_raw;     /* [B][3][n]                                                           */
+    uint8_t* trg_ok;           /* [B][n]                                                              */
+    uint8_t* src_ok;           /* [n]                                                                 */
+    int64_t* full_mask;        /* [B][n]                                                              */
+    int64_t* seg_ids;          /* [n]                                                                 */
+} SpbStats;
+
+/* ============================ geometry build (once per keyframe) ============================== */
+
+/* Pass 1: per (segment,row) population count of the bool masks (N,H,W).
+ * Replaces the first half of torch.where in core/dense_optim.py:98-103. */
+int spb_compact_count(const uint8_t* masks, int N, int H, int W, int32_t* row_cnt, void* stream);
+
+/* Pass 2: exclusive scan of row counts -> row offsets in the padded point array, CSR pointers.
+ * totals[0] = P (unpadded), totals[1] = padded length. Single CTA. */
+int spb_compact_scan(const int32_t* row_cnt, int N, int H, int32_t* row_off, int32_t* seg_ptr,
+                     int32_t* seg_ptr_pad, int32_t* totals, void* stream);
+
+/* Pass 3: ordered scatter (segment,row,col order == torch.where order) of packed pixel
+ * coordinates and raw log-depth; also the per-segment keypoint pixel and log-depth at the
+ * keypoint (core/dense_optim.py:51-64, tool/point_utils.py:37-40) and the static
+ * source-validity bit (core/dense_optim.py:128-130,146 applied to the point's own pixel).
+ * logd_seg_stride = H*W for per-segment log-depth, 0 for a shared (H,W) map. */
+int spb_compact_fill(const uint8_t* masks, const float* logd, int64_t logd_seg_stride,
+                     const float* keypoints, const float* K, int N, int H, int W,
+                     const int32_t* row_off, const int32_t* seg_ptr_pad, uint32_t* uv, float* L,
+                     float* seg_lkp, int32_t* kp_rc, void* stream);
+
+/* planar (3,Hl,Wl) -> RGBA-interleaved [Hl][Wl][4]; n_img images, src stride in floats. */
+int spb_pack_rgba(const float* planar, int64_t img_stride, int n_img, int Hl, int Wl, float* rgba,
+                  void* stream);
+
+/* cached source samples: bilinear sample of the source level image at every point's own
+ * pixel scaled to the level (core/dense_optim.py:315-317 / :190-192). out = [3][n_pad]. */
+int spb_sample_source(const SpbGeom* geom, const float* src_planar, int Hl, int Wl, float* out,
+                      void* stream);
+
+/* ================================ per-iteration hot path ====================================== */
+
+/* Fused residual + first-order gradient for B pairs sharing geometry `geom` (host struct, device
+ * pointers inside), replacing photomeric_cost / photomeric_cost_batch forward AND backward
+ * (core/dense_optim.py:265-363, core/dense_optim_batch.py:50-147).
+ *   pairs      : HOST array of B pair descriptors (B <= 16), passed to the kernel by value
+ *   work       : device workspace, spb_workspace_floats(geom, B, 0) floats
+ *   out_pair   : [B][SPB_PAIR_NOUT]      out_gk : [B][n_seg] d cost_j / d k_b
+ *   stats      : NULL or per-point outputs                                                      */
+int spb_cost_grad(const SpbGeom* geom, const SpbPair* pairs, int B, float* work, float* out_pair,
+                  float* out_gk, const SpbStats* stats, void* stream);
+
+/* Same for pre-lifted points (tracking): photomeric_cost_precomputed, core/dense_optim.py:365-403.
+ * src_pts [P][3], src_px [3][P] planar, src_ok [P]; dims = geometry grid (H,W) used for
+ * normalisation.  No log-depth gradient.  out_pair : [SPB_PAIR_NOUT]. */
+int spb_cost_grad_points(const float* src_pts, const float* src_px, const uint8_t* src_ok, int P,
+                         int H, int W, const SpbPair* pair, float* work, float* out_pair,
+                         void* stream);
+
+/* workspace size in floats for B pairs over `geom` (gn = 0 gradient mode, 1 GN mode) */
+int64_t spb_workspace_floats(const SpbGeom* geom, int B, int gn);
+int64_t spb_workspace_floats_points(int P);
+
+/* ============================ batched GN / LM solver (device arrays) ========================== */
+
+/* One IRLS Gauss-Newton accumulation over n_pairs independent problems whose descriptors live in
+ * DEVICE memory (geoms[], pairs[]); writes per-pair arrowhead blocks.  No reference counterpart
+ * (the reference uses Adam + autograd) -- oracle: oracle/closed_form.py.
+ *   max_tiles : max over problems of geom.n_tiles (grid sizing)
+ *   out_pair  : [n_pairs][SPB_GN_PAIR_NOUT]   out_seg : [seg_total][SPB_GN_SEG_NOUT]
+ *   seg_off   : [n_pairs] offset of each problem's segments in out_seg                          */
+int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off,
+                      int n_pairs, int max_tiles, float irls_eps, int with_affine, float* work,
+                      int64_t work_stride, float* out_pair, float* out_seg, void* stream);
+
+/* Gradient mode over the same device-resident descriptors (batched Adam-parity iterations):
+ * out_pair [n_pairs][SPB_PAIR_NOUT], out_gk [seg_total] (indexed seg_off[pair] + b). */
+int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off,
+                        int n_pairs, int max_tiles, float* work, int64_t work_stride,
+                        float* out_pair, float* out_gk, void* stream);
+
+/* CTAs per pair the batched launches use for (max_tiles, n_pairs): the workspace stride must be
+ * >= ctas * nacc + max_tiles * nseg floats (nacc/nseg = 16/1 gradient, 47/10 GN). */
+int spb_gn_ctas(int max_tiles, int n_pairs);
+
+/* Damped Schur-complement solve (float64) + SE(3) retraction T <- Exp(xi) T + log-depth update for
+ * n_pairs problems, with LM accept/reject bookkeeping kept on the device:
+ *   lm_state [n_pairs][SPB_LM_NSTATE] = {lambda, accepted cost, initialised, n_accept, n_reject,
+ *                                        last cost, |step|, -}
+ *   saved_*  : last accepted parameters + system (sizes from spb_lm_saved_floats)
+ * poses [n_pairs][16], k[seg_total] and aff_trg [n_pairs][2] (may be NULL) are updated in place. */
+#define SPB_LM_NSTATE 8
+int spb_lm_saved_floats(int n_pairs, int seg_total, int64_t* pair_floats, int64_t* seg_floats);
+int spb_lm_update(const float* gn_pair, const float* gn_seg, const int32_t* seg_off,
+                  const int32_t* seg_cnt, int n_pairs, int with_affine, float* poses, float* k,
+                  float* aff_trg, float* lm_state, float* saved_pair, float* saved_seg, void* stream);
+
+/* ================================== geometry-only entry points ================================ */
+
+/* unproject_kf_to_depths (core/dense_optim.py:164-174): dense (N,H,W) depth, exp((L+shift)*mask).
+ * Dense on purpose: depth completion consumes the dense tensor. */
+int spb_dense_depths(const uint8_t* masks, const float* logd, int64_t logd_seg_stride,
+                     const float* seg_lkp, const float* k, int N, int H, int W, float* out,
+                     void* stream);
+
+/* estimate_depth_kf_native (core/depth_render.py:7-21 + core/ops.py:59-96): z-splat of the lifted
+ * keyframe into view `pose`.  mean = 0: deterministic last-writer-wins in point order (the CPU
+ * semantics of scatter_); mean = 1: scatter_reduce 'mean' including the initial zero.
+ * keys: [H*W] uint64 scratch (zeroed by the call); out: [H][W]. */
+int spb_depth_splat(const SpbGeom* geom, const float* k, const float* pose /* NULL = identity */,
+                    int mean, unsigned long long* keys, float* sum, float* out, void* stream);
+
+/* lifted points of a keyframe: src_pts [n][3] (core/dense_optim.py:176-200) */
+int spb_lift_points(const SpbGeom* geom, const float* k, float* src_pts, int64_t* seg_ids,
+                    uint8_t* src_ok, void* stream);
+
+/* version / build info */
+int spb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPB200_H */

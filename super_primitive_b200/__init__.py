@@ -1,0 +1,29 @@
+"""super_primitive_b200 -- B200-native (sm_100a) dense photometric alignment, a drop-in for the hot
+path of makezur/super_primitive (``core.dense_optim``, ``core.dense_optim_batch``,
+``core.depth_render``).  See DESIGN.md / INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import sys
+import types
+
+__version__ = "0.1.0"
+
+_ALIASES = ("dense_optim", "dense_optim_batch", "depth_render", "ops")
+
+
+def install_as_core(force=True):
+    """Make ``import core.dense_optim`` (etc.) resolve to this package so the reference's callers
+    (odometery/, depth_completion/, gui/, tool/viz.py) run unchanged.  Call before importing them.
+    The reference's remaining ``core`` modules (cost_utils, normal_cost) are not needed by callers."""
+    import importlib
+    pkg = sys.modules.get("core")
+    if pkg is None or force:
+        pkg = types.ModuleType("core")
+        pkg.__path__ = []          # namespace-like package
+        sys.modules["core"] = pkg
+    for name in _ALIASES:
+        mod = importlib.import_module(f"{__name__}.{name}")
+        sys.modules[f"core.{name}"] = mod
+        setattr(pkg, name, mod)
+    return pkg

@@ -1,0 +1,108 @@
+"""ctypes binding of the C-ABI shared library ``csrc/libspb200.so`` (include/spb200.h).
+
+The product path has no CPU fallback: if the library is missing or a call fails, an
+exception is raised (``NativeLibraryError`` / ``RuntimeError``).  Loading the library does not
+create a CUDA context.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libspb200.so")
+
+TILE = 128
+PAD = 4
+PAIR_NOUT = 16
+GN_PAIR_NOUT = 48
+GN_SEG_NOUT = 10
+GN_NA = 36
+LM_NSTATE = 8
+MAX_INLINE_PAIRS = 16
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class SpbGeom(C.Structure):
+    _fields_ = [("uv", C.c_void_p), ("logd", C.c_void_p), ("tiles", C.c_void_p),
+                ("seg_tile", C.c_void_p), ("seg_lkp", C.c_void_p), ("K", C.c_void_p),
+                ("n_pts", C.c_int32), ("n_pad", C.c_int32), ("n_seg", C.c_int32),
+                ("n_tiles", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
+class SpbPair(C.Structure):
+    _fields_ = [("trg_rgba", C.c_void_p), ("src_rgb", C.c_void_p), ("K_trg", C.c_void_p),
+                ("pose", C.c_void_p), ("k", C.c_void_p), ("aff_src", C.c_void_p),
+                ("aff_trg", C.c_void_p), ("geom", C.c_int32), ("Hl", C.c_int32),
+                ("Wl", C.c_int32), ("tau", C.c_float)]
+
+
+class SpbStats(C.Structure):
+    _fields_ = [("src_pts", C.c_void_p), ("moved_pts", C.c_void_p), ("trg_px", C.c_void_p),
+                ("residual_raw", C.c_void_p), ("trg_ok", C.c_void_p), ("src_ok", C.c_void_p),
+                ("full_mask", C.c_void_p), ("seg_ids", C.c_void_p)]
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_PROTOS = {
+    "spb_compact_count": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "spb_compact_scan": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "spb_compact_fill": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spb_pack_rgba": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
+    "spb_sample_source": (_i, [C.POINTER(SpbGeom), _vp, _i, _i, _vp, _vp]),
+    "spb_cost_grad": (_i, [C.POINTER(SpbGeom), C.POINTER(SpbPair), _i, _vp, _vp, _vp,
+                           C.POINTER(SpbStats), _vp]),
+    "spb_cost_grad_points": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SpbPair), _vp, _vp, _vp]),
+    "spb_workspace_floats": (_i64, [C.POINTER(SpbGeom), _i, _i]),
+    "spb_workspace_floats_points": (_i64, [_i]),
+    "spb_gn_ctas": (_i, [_i, _i]),
+    "spb_gn_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _vp, _i64, _vp, _vp, _vp]),
+    "spb_grad_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp]),
+    "spb_lm_saved_floats": (_i, [_i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
+    "spb_lm_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spb_dense_depths": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "spb_depth_splat": (_i, [C.POINTER(SpbGeom), _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "spb_lift_points": (_i, [C.POINTER(SpbGeom), _vp, _vp, _vp, _vp, _vp]),
+    "spb_version": (_i, []),
+}
+
+EXPORTS = tuple(_PROTOS)
+_lib = None
+
+
+def lib():
+    """The loaded library; raises NativeLibraryError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or super_primitive_b200/csrc/build.sh).  There is no CPU fallback.")
+        try:
+            handle = C.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+        for name, (res, args) in _PROTOS.items():
+            try:
+                fn = getattr(handle, name)
+            except AttributeError as e:
+                raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        if status > 0:
+            raise RuntimeError(f"{what}: CUDA error {status}")
+        raise RuntimeError(f"{what}: invalid arguments (code {status})")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,621 @@
+// Fused per-iteration kernels of the dense photometric alignment path (sm_100a).
+//
+// One launch evaluates, for every point of every (source geometry, target image) pair:
+//   depth = exp(L + k_b - L_kp)           core/dense_optim.py:38-86
+//   X = unproject(u, v, depth)            core/dense_optim.py:19-35
+//   Y = R X + t                           core/dense_optim.py:117-122, core/ops.py:5-17
+//   (u', v') guarded pinhole projection   core/ops.py:19-40
+//   normalise by geometry dims, validity  tool/point_utils.py:31-35, core/dense_optim.py:128-162
+//   bilinear sample (align_corners, zeros padding) of the level image   core/dense_optim.py:134-136
+//   affine brightness, masked residual, L1 mean                          core/dense_optim.py:202-261
+// and, in the same pass, either the first-order gradient w.r.t. (pose 4x4, k, affine) that the
+// reference obtains by autograd (MODE_GRAD), or the IRLS Gauss-Newton arrowhead blocks (MODE_GN).
+//
+// Layout: points are stored compacted in (segment,row,col) order; a warp processes one tile
+// (<= SPB_TILE points of ONE segment), each lane SPB_PPT points strided by 32 so the streaming
+// reads (uv, logd, cached source rgb) are fully coalesced.  The target image is RGBA-interleaved
+// so one bilinear tap is one 16-byte load.  Reductions are deterministic: per-warp shuffle ->
+// per-CTA partial -> fixed-order finalize kernel; no float atomics.
+#include "spb_common.cuh"
+
+enum { MODE_GRAD = 0, MODE_GN = 1 };
+
+template <int NACC>
+__device__ __forceinline__ void block_reduce_store(float (&acc)[NACC], float* s_red, float* dst) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        const float v = warp_sum(acc[i]);
+        if (lane == 0) s_red[warp * NACC + i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NACC; i += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < SPB_WARPS; ++w) v += s_red[w * NACC + i];
+        dst[i] = v;
+    }
+}
+
+struct PointOut {   // where the optional per-point statistics go
+    const SpbStats* st;
+    int pair;
+    int n;
+};
+
+// ------------------------------------------------------------------------------------------------
+// The per-point evaluation shared by every variant.
+//   GEOMETRY: X, RX(+t)=Y, projection, validity.  Then taps + residual.
+// Accumulators:
+//   MODE_GRAD: acc[16] = cost, gt[3], gR[9], ga, gb, nvalid ; seg[1] = gk
+//   MODE_GN  : acc[NP*(NP+1)/2 + NP + 3] ; seg[NP + 2]
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int NP, bool STATS, int NACC, int NSEG>
+__device__ __forceinline__ void eval_point(const float* __restrict__ c, const float4* __restrict__ trg,
+                                           int Wl, int Hl, float Xx, float Xy, float Xz, bool sok,
+                                           float Is0, float Is1, float Is2, float irls_eps,
+                                           float (&acc)[NACC], float (&seg)[NSEG],
+                                           const PointOut& po, int pidx) {
+    const float RXx = fmaf(c[C_R + 0], Xx, fmaf(c[C_R + 1], Xy, c[C_R + 2] * Xz));
+    const float RXy = fmaf(c[C_R + 3], Xx, fmaf(c[C_R + 4], Xy, c[C_R + 5] * Xz));
+    const float RXz = fmaf(c[C_R + 6], Xx, fmaf(c[C_R + 7], Xy, c[C_R + 8] * Xz));
+    const float Yx = RXx + c[C_T + 0];
+    const float Yy = RXy + c[C_T + 1];
+    const float Yz = RXz + c[C_T + 2];
+    const bool live = fabsf(Yz) > 1e-6f;                       // guarded reciprocal, core/ops.py:22,33-34
+    const float zi = live ? (1.0f / Yz) : 1e-6f;
+    const float up = fmaf(Yx * c[C_FXT], zi, c[C_CXT]);
+    const float vp = fmaf(Yy * c[C_FYT], zi, c[C_CYT]);
+    const float xn = fmaf(up, c[C_TIW], -1.0f);
+    const float yn = fmaf(vp, c[C_TIH], -1.0f);
+    const bool tok = (fabsf(xn) <= 0.99f) && (fabsf(yn) <= 0.99f) && (Yz > c[C_TAU]);
+    const bool m = tok && sok;
+    const float ix = (xn + 1.0f) * c[C_SX];
+    const float iy = (yn + 1.0f) * c[C_SY];
+
+    if constexpr (STATS) {
+        // slow path: materialise the reference's per-point statistics (core/dense_optim.py:347-361)
+        const SpbStats& st = *po.st;
+        const size_t n = (size_t)po.n, j = (size_t)po.pair;
+        if (st.moved_pts) {
+            float* o = st.moved_pts + (j * n + pidx) * 3;
+            o[0] = Yx; o[1] = Yy; o[2] = Yz;
+        }
+        if (st.trg_ok) st.trg_ok[j * n + pidx] = tok ? 1 : 0;
+        if (st.full_mask) st.full_mask[j * n + pidx] = m ? 1 : 0;
+        float v[3] = {0.f, 0.f, 0.f};
+        if (isfinite(ix) && isfinite(iy)) {
+            const float fxf = floorf(ix), fyf = floorf(iy);
+            // clamp before the int conversion so wild coordinates cannot overflow
+            const int x0 = (int)fminf(fmaxf(fxf, -2.0f), (float)Wl + 1.0f);
+            const int y0 = (int)fminf(fmaxf(fyf, -2.0f), (float)Hl + 1.0f);
+            const float fx = ix - fxf, fy = iy - fyf;
+            const float4 nw = tap_rgba(trg, x0, y0, Wl, Hl), ne = tap_rgba(trg, x0 + 1, y0, Wl, Hl);
+            const float4 sw = tap_rgba(trg, x0, y0 + 1, Wl, Hl), se = tap_rgba(trg, x0 + 1, y0 + 1, Wl, Hl);
+            float d0, d1;
+            blend(nw.x, ne.x, sw.x, se.x, fx, fy, v[0], d0, d1);
+            blend(nw.y, ne.y, sw.y, se.y, fx, fy, v[1], d0, d1);
+            blend(nw.z, ne.z, sw.z, se.z, fx, fy, v[2], d0, d1);
+        }
+        const float Is[3] = {Is0, Is1, Is2};
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float Ia = fmaf(c[C_EA], v[ch], c[C_BB]);
+            if (st.trg_px) st.trg_px[(j * 3 + ch) * n + pidx] = Ia;
+            if (st.residual_raw) st.residual_raw[(j * 3 + ch) * n + pidx] = m ? (Is[ch] - Ia) : 0.0f;
+        }
+    }
+
+    if (!m) return;
+
+    // fast path: valid => |xn|,|yn| <= 0.99 => all four taps are inside the image
+    const float fxf = floorf(ix), fyf = floorf(iy);
+    const int x0 = (int)fxf, y0 = (int)fyf;
+    const float fx = ix - fxf, fy = iy - fyf;
+    const float4* p0 = trg + (size_t)y0 * Wl + x0;
+    const float4 nw = __ldg(p0), ne = __ldg(p0 + 1);
+    const float4 sw = __ldg(p0 + Wl), se = __ldg(p0 + Wl + 1);
+
+    float I[3], dx[3], dy[3];
+    blend(nw.x, ne.x, sw.x, se.x, fx, fy, I[0], dx[0], dy[0]);
+    blend(nw.y, ne.y, sw.y, se.y, fx, fy, I[1], dx[1], dy[1]);
+    blend(nw.z, ne.z, sw.z, se.z, fx, fy, I[2], dx[2], dy[2]);
+    const float Is[3] = {Is0, Is1, Is2};
+    const float ea = c[C_EA], bb = c[C_BB];
+
+    if constexpr (MODE == MODE_GRAD) {
+        // d|r|/dI_t = -e^{-a} sign(r);  accumulate sign-weighted image slopes first
+        float gx = 0.f, gy = 0.f, ga = 0.f, gb = 0.f, cost = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float r = Is[ch] - fmaf(ea, I[ch], bb);
+            cost += fabsf(r);
+            const float s = (r > 0.f) ? 1.0f : ((r < 0.f) ? -1.0f : 0.0f);
+            gx = fmaf(s, dx[ch], gx);
+            gy = fmaf(s, dy[ch], gy);
+            ga = fmaf(s, I[ch], ga);
+            gb += s;
+        }
+        const float gu = -ea * c[C_KX] * gx;          // d cost / d u'
+        const float gv = -ea * c[C_KY] * gy;
+        const float gYx = gu * c[C_FXT] * zi;
+        const float gYy = gv * c[C_FYT] * zi;
+        const float gYz = live ? -(gYx * Yx + gYy * Yy) * zi : 0.0f;
+        acc[0] += cost;
+        acc[1] += gYx; acc[2] += gYy; acc[3] += gYz;
+        acc[4] = fmaf(gYx, Xx, acc[4]);  acc[5] = fmaf(gYx, Xy, acc[5]);  acc[6] = fmaf(gYx, Xz, acc[6]);
+        acc[7] = fmaf(gYy, Xx, acc[7]);  acc[8] = fmaf(gYy, Xy, acc[8]);  acc[9] = fmaf(gYy, Xz, acc[9]);
+        acc[10] = fmaf(gYz, Xx, acc[10]); acc[11] = fmaf(gYz, Xy, acc[11]); acc[12] = fmaf(gYz, Xz, acc[12]);
+        acc[13] = fmaf(ea, ga, acc[13]);
+        acc[14] -= gb;
+        acc[15] += 1.0f;
+        if constexpr (NSEG > 0) seg[0] += fmaf(gYx, RXx, fmaf(gYy, RXy, gYz * RXz));
+    } else {
+        // IRLS normal equations: r_c = I_s - (e^{-a} I_c + b); J_c = -(e^{-a}) (dIx kx du' + dIy ky dv')
+        float Guu = 0.f, Guv = 0.f, Gvv = 0.f, hu = 0.f, hv = 0.f, cost = 0.f, wcost = 0.f;
+        float Aau = 0.f, Aav = 0.f, Abu = 0.f, Abv = 0.f, Aaa = 0.f, Aab = 0.f, Abb = 0.f, ha = 0.f, hb = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float r = Is[ch] - fmaf(ea, I[ch], bb);
+            const float ar = fabsf(r);
+            const float w = __fdividef(1.0f, fmaxf(ar, irls_eps));
+            cost += ar;
+            wcost = fmaf(w * r, r, wcost);
+            const float wu = w * dx[ch], wv = w * dy[ch];
+            Guu = fmaf(wu, dx[ch], Guu);
+            Guv = fmaf(wu, dy[ch], Guv);
+            Gvv = fmaf(wv, dy[ch], Gvv);
+            hu = fmaf(wu, r, hu);
+            hv = fmaf(wv, r, hv);
+            if constexpr (NP == 8) {
+                const float ja = ea * I[ch];      // d r / d a_t ; d r / d b_t = -1
+                Aau = fmaf(wu, ja, Aau); Aav = fmaf(wv, ja, Aav);
+                Abu -= wu; Abv -= wv;
+                Aaa = fmaf(w * ja, ja, Aaa); Aab = fmaf(-w, ja, Aab); Abb += w;
+                ha = fmaf(w * ja, r, ha); hb = fmaf(-w, r, hb);
+            }
+        }
+        const float cu = -ea * c[C_KX], cv = -ea * c[C_KY];
+        Guu *= cu * cu; Guv *= cu * cv; Gvv *= cv * cv; hu *= cu; hv *= cv;
+        // mu = d u'/d(xi,k), mv = d v'/d(xi,k); xi = (tau, phi), left perturbation T <- Exp(xi) T
+        const float xb = Yx * zi, yb = Yy * zi;
+        const float zl = live ? 1.0f : 0.0f;
+        const float fu = c[C_FXT] * zi, fv = c[C_FYT] * zi;
+        float mu[7], mv[7];
+        mu[0] = fu;  mu[1] = 0.f; mu[2] = -fu * xb * zl;
+        mu[3] = mu[2] * Yy;               mu[4] = fu * Yz - mu[2] * Yx;   mu[5] = -fu * Yy;
+        mv[0] = 0.f; mv[1] = fv;  mv[2] = -fv * yb * zl;
+        mv[3] = -fv * Yz + mv[2] * Yy;    mv[4] = -mv[2] * Yx;            mv[5] = fv * Yx;
+        mu[6] = fmaf(mu[0], RXx, mu[2] * RXz);
+        mv[6] = fmaf(mv[1], RXy, mv[2] * RXz);
+        float pu[7], pv[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            pu[i] = fmaf(Guu, mu[i], Guv * mv[i]);
+            pv[i] = fmaf(Guv, mu[i], Gvv * mv[i]);
+        }
+        // upper triangle of the NPxNP pose block, row-major packed
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = i; j < 6; ++j) { acc[q] = fmaf(mu[i], pu[j], fmaf(mv[i], pv[j], acc[q])); ++q; }
+            if constexpr (NP == 8) {
+                acc[q] = fmaf(mu[i], cu * Aau, fmaf(mv[i], cv * Aav, acc[q])); ++q;
+                acc[q] = fmaf(mu[i], cu * Abu, fmaf(mv[i], cv * Abv, acc[q])); ++q;
+            }
+        }
+        if constexpr (NP == 8) { acc[q++] += Aaa; acc[q++] += Aab; acc[q++] += Abb; }
+        constexpr int NA = NP * (NP + 1) / 2;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc[NA + i] = fmaf(mu[i], hu, fmaf(mv[i], hv, acc[NA + i]));
+        if constexpr (NP == 8) { acc[NA + 6] += ha; acc[NA + 7] += hb; }
+        acc[NA + NP + 0] += cost;
+        acc[NA + NP + 1] += wcost;
+        acc[NA + NP + 2] += 1.0f;
+        if constexpr (NSEG > 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) seg[i] = fmaf(mu[i], pu[6], fmaf(mv[i], pv[6], seg[i]));
+            if constexpr (NP == 8) {
+                seg[6] = fmaf(mu[6], cu * Aau, fmaf(mv[6], cv * Aav, seg[6]));
+                seg[7] = fmaf(mu[6], cu * Abu, fmaf(mv[6], cv * Abv, seg[7]));
+            }
+            seg[NP] = fmaf(mu[6], pu[6], fmaf(mv[6], pv[6], seg[NP]));
+            seg[NP + 1] = fmaf(mu[6], hu, fmaf(mv[6], hv, seg[NP + 1]));
+        }
+    }
+}
+
+template <int MODE, int NP>
+struct Sizes {
+    static constexpr int NACC = (MODE == MODE_GRAD) ? SPB_PAIR_NOUT : (NP * (NP + 1) / 2 + NP + 3);
+    static constexpr int NSEG = (MODE == MODE_GRAD) ? 1 : (NP + 2);
+};
+
+// ------------------------------------------------------------------------------------------------
+// Compact-geometry variant.  grid = (ctas_per_pair, n_pairs)
+//   part_pair : [pair][cta][NACC]      part_seg : [pair][tile][NSEG]
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int NP, bool STATS>
+__device__ __forceinline__ void align_body(const SpbGeom& g, const SpbPair& pr, int pair, float irls_eps,
+                                           float* __restrict__ part_pair, float* __restrict__ part_seg,
+                                           const SpbStats* stats) {
+    constexpr int NACC = Sizes<MODE, NP>::NACC;
+    constexpr int NSEG = Sizes<MODE, NP>::NSEG;
+    __shared__ float s_ctx[C_N];
+    __shared__ float s_red[SPB_WARPS * NACC];
+    if (threadIdx.x < 32) fill_ctx(s_ctx, pr, g.K, g.H, g.W);
+    __syncthreads();
+    const float* c = s_ctx;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4* trg = reinterpret_cast<const float4*>(pr.trg_rgba);
+    const int Wl = pr.Wl, Hl = pr.Hl;
+    const float* sr0 = pr.src_rgb;
+    const float* sr1 = pr.src_rgb + g.n_pad;
+    const float* sr2 = pr.src_rgb + 2 * (size_t)g.n_pad;
+    const int4* tiles = reinterpret_cast<const int4*>(g.tiles);
+    PointOut po{stats, pair, g.n_pts};
+
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+
+    const int wstride = gridDim.x * SPB_WARPS;
+    for (int t = blockIdx.x * SPB_WARPS + warp; t < g.n_tiles; t += wstride) {
+        const int4 td = __ldg(tiles + t);
+        const int sidx = td.x, start = td.y, cnt = td.z;
+        const float shift = __ldg(pr.k + sidx) - __ldg(g.seg_lkp + sidx);
+        float seg[NSEG];
+#pragma unroll
+        for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
+
+        // issue all streaming loads of this lane's points first (memory-level parallelism)
+        uint32_t w[SPB_PPT];
+        float L[SPB_PPT], s0[SPB_PPT], s1[SPB_PPT], s2[SPB_PPT];
+#pragma unroll
+        for (int j = 0; j < SPB_PPT; ++j) {
+            const int i = j * 32 + lane;
+            const bool on = i < cnt;
+            const int p = start + (on ? i : 0);
+            w[j] = __ldg(g.uv + p);
+            L[j] = __ldg(g.logd + p);
+            s0[j] = __ldg(sr0 + p); s1[j] = __ldg(sr1 + p); s2[j] = __ldg(sr2 + p);
+        }
+#pragma unroll
+        for (int j = 0; j < SPB_PPT; ++j) {
+            const int i = j * 32 + lane;
+            if (i < cnt) {
+                const float u = (float)(w[j] & 0xffffu);
+                const float v = (float)((w[j] >> 16) & 0x7fffu);
+                const float z = expf(L[j] + shift);
+                const float Xx = (u - c[C_CX]) * z * c[C_IFX];
+                const float Xy = (v - c[C_CY]) * z * c[C_IFY];
+                const bool sok = (w[j] >> 31) && (z > 1e-7f);
+                if constexpr (STATS) {
+                    if (pair == 0 && stats->src_pts) {
+                        float* o = stats->src_pts + (size_t)(td.w + i) * 3;
+                        o[0] = Xx; o[1] = Xy; o[2] = z;
+                    }
+                }
+                eval_point<MODE, NP, STATS, NACC, NSEG>(c, trg, Wl, Hl, Xx, Xy, z, sok, s0[j], s1[j], s2[j],
+                                                        irls_eps, acc, seg, po, td.w + i);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NSEG; ++i) {
+            const float v = warp_sum(seg[i]);
+            if (lane == 0) part_seg[(size_t)t * NSEG + i] = v;
+        }
+    }
+    block_reduce_store<NACC>(acc, s_red, part_pair + (size_t)blockIdx.x * NACC);
+}
+
+struct PairPack {
+    SpbPair p[16];
+};
+
+// B pairs over one geometry, descriptors by value (Python per-call path: no descriptor upload)
+template <int MODE, int NP, bool STATS>
+__global__ void __launch_bounds__(SPB_THREADS, 2)
+k_align_inline(const __grid_constant__ SpbGeom g, const __grid_constant__ PairPack pack, float irls_eps,
+               float* __restrict__ work, SpbStats stats) {
+    constexpr int NACC = Sizes<MODE, NP>::NACC;
+    constexpr int NSEG = Sizes<MODE, NP>::NSEG;
+    const int pair = blockIdx.y;
+    const size_t stride = (size_t)gridDim.x * NACC + (size_t)g.n_tiles * NSEG;
+    float* base = work + pair * stride;
+    align_body<MODE, NP, STATS>(g, pack.p[pair], pair, irls_eps, base, base + (size_t)gridDim.x * NACC,
+                                STATS ? &stats : nullptr);
+}
+
+// n_pairs independent problems, descriptors in device memory (batched solver / benchmark path)
+template <int MODE, int NP>
+__global__ void __launch_bounds__(SPB_THREADS, 2)
+k_align_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs, float irls_eps,
+               float* __restrict__ work, int64_t work_stride) {
+    constexpr int NACC = Sizes<MODE, NP>::NACC;
+    const int pair = blockIdx.y;
+    __shared__ SpbPair s_pr;
+    __shared__ SpbGeom s_g;
+    if (threadIdx.x == 0) {
+        s_pr = pairs[pair];
+        s_g = geoms[s_pr.geom];
+    }
+    __syncthreads();
+    float* base = work + pair * work_stride;
+    align_body<MODE, NP, false>(s_g, s_pr, pair, irls_eps, base, base + (size_t)gridDim.x * NACC, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: fixed-order reduction of the partials
+// ------------------------------------------------------------------------------------------------
+__global__ void k_finalize_grad(const __grid_constant__ SpbGeom g, int ctas, const float* __restrict__ work,
+                                float* __restrict__ out_pair, float* __restrict__ out_gk) {
+    const int pair = blockIdx.x;
+    const size_t stride = (size_t)ctas * SPB_PAIR_NOUT + (size_t)g.n_tiles;
+    const float* pp = work + pair * stride;
+    const float* ps = pp + (size_t)ctas * SPB_PAIR_NOUT;
+    const float norm = 1.0f / (3.0f * (float)g.n_pts);
+    if (threadIdx.x < SPB_PAIR_NOUT) {
+        float v = 0.f;
+        for (int cta = 0; cta < ctas; ++cta) v += pp[(size_t)cta * SPB_PAIR_NOUT + threadIdx.x];
+        out_pair[pair * SPB_PAIR_NOUT + threadIdx.x] = (threadIdx.x == 15) ? v : v * norm;
+    }
+    for (int b = threadIdx.x; b < g.n_seg; b += blockDim.x) {
+        float v = 0.f;
+        const int t1 = g.seg_tile[b + 1];
+        for (int t = g.seg_tile[b]; t < t1; ++t) v += ps[t];
+        out_gk[(size_t)pair * g.n_seg + b] = v * norm;
+    }
+}
+
+template <int NP>
+__global__ void k_finalize_gn(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
+                              const int32_t* __restrict__ seg_off, int ctas, const float* __restrict__ work,
+                              int64_t work_stride, float* __restrict__ out_pair, float* __restrict__ out_seg) {
+    constexpr int NACC = Sizes<MODE_GN, NP>::NACC;
+    constexpr int NSEG = Sizes<MODE_GN, NP>::NSEG;
+    constexpr int NA = NP * (NP + 1) / 2;
+    const int pair = blockIdx.x;
+    const SpbGeom& g = geoms[pairs[pair].geom];
+    const float* pp = work + pair * work_stride;
+    const float* ps = pp + (size_t)ctas * NACC;
+    float* op = out_pair + (size_t)pair * SPB_GN_PAIR_NOUT;
+    if (threadIdx.x < NACC) {
+        float v = 0.f;
+        for (int cta = 0; cta < ctas; ++cta) v += pp[(size_t)cta * NACC + threadIdx.x];
+        // scatter into the fixed 8-column layout
+        const int i = threadIdx.x;
+        if (NP == 8) {
+            op[i] = v;
+        } else {
+            if (i < NA) {            // (r,c) in the 6x6 triangle -> index in the 8x8 triangle
+                int r = 0, rem = i;
+                while (rem >= 6 - r) { rem -= 6 - r; ++r; }
+                const int cc = r + rem;
+                const int idx8 = r * 8 - r * (r - 1) / 2 + (cc - r);
+                op[idx8] = v;
+            } else if (i < NA + 6) {
+                op[SPB_GN_NA + (i - NA)] = v;
+            } else {
+                op[SPB_GN_NA + 8 + (i - NA - 6)] = v;
+            }
+        }
+    }
+    if (NP == 6 && threadIdx.x < SPB_GN_PAIR_NOUT) {
+        // zero the affine rows/cols + pad that the 6-column accumulation does not touch
+        const int i = threadIdx.x;
+        bool touched = false;
+        if (i < SPB_GN_NA) {
+            int r = 0, rem = i;
+            while (rem >= 8 - r) { rem -= 8 - r; ++r; }
+            const int cc = r + rem;
+            touched = (r < 6 && cc < 6);
+        } else if (i < SPB_GN_NA + 8) {
+            touched = (i - SPB_GN_NA) < 6;
+        } else {
+            touched = (i - SPB_GN_NA - 8) < 3;
+        }
+        if (!touched) op[i] = 0.f;
+    }
+    if (NP == 8 && threadIdx.x == SPB_GN_PAIR_NOUT - 1) op[threadIdx.x] = 0.f;
+    const int so = seg_off[pair];
+    for (int b = threadIdx.x; b < g.n_seg; b += blockDim.x) {
+        float v[NSEG];
+#pragma unroll
+        for (int i = 0; i < NSEG; ++i) v[i] = 0.f;
+        const int t1 = g.seg_tile[b + 1];
+        for (int t = g.seg_tile[b]; t < t1; ++t) {
+#pragma unroll
+            for (int i = 0; i < NSEG; ++i) v[i] += ps[(size_t)t * NSEG + i];
+        }
+        float* os = out_seg + (size_t)(so + b) * SPB_GN_SEG_NOUT;
+        if (NP == 8) {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) os[i] = v[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) os[i] = v[i];
+            os[6] = 0.f; os[7] = 0.f; os[8] = v[6]; os[9] = v[7];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pre-lifted points variant (tracking): X given, no log-depth gradient
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPB_THREADS, 2)
+k_align_points(const float* __restrict__ src_pts, const float* __restrict__ src_px,
+               const uint8_t* __restrict__ src_ok, int P, int H, int W, const __grid_constant__ SpbPair pr,
+               float* __restrict__ work) {
+    constexpr int NACC = SPB_PAIR_NOUT;
+    __shared__ float s_ctx[C_N];
+    __shared__ float s_red[SPB_WARPS * NACC];
+    __shared__ float s_K[9];
+    if (threadIdx.x < 9) s_K[threadIdx.x] = (threadIdx.x % 4 == 0) ? 1.f : 0.f;   // unused source intrinsics
+    __syncthreads();
+    if (threadIdx.x < 32) fill_ctx(s_ctx, pr, s_K, H, W);
+    __syncthreads();
+    const float* c = s_ctx;
+    const float4* trg = reinterpret_cast<const float4*>(pr.trg_rgba);
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+    float none[1] = {0.f};
+    PointOut po{nullptr, 0, P};
+    const int stride = gridDim.x * blockDim.x;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += stride) {
+        const float Xx = __ldg(src_pts + 3 * (size_t)p), Xy = __ldg(src_pts + 3 * (size_t)p + 1),
+                    Xz = __ldg(src_pts + 3 * (size_t)p + 2);
+        const bool sok = __ldg(src_ok + p) != 0;
+        const float i0 = __ldg(src_px + p), i1 = __ldg(src_px + (size_t)P + p), i2 = __ldg(src_px + 2 * (size_t)P + p);
+        eval_point<MODE_GRAD, 6, false, NACC, 0 + 1>(c, trg, pr.Wl, pr.Hl, Xx, Xy, Xz, sok, i0, i1, i2, 0.f, acc,
+                                                     none, po, p);
+    }
+    block_reduce_store<NACC>(acc, s_red, work + (size_t)blockIdx.x * NACC);
+}
+
+__global__ void k_finalize_points(int ctas, int P, const float* __restrict__ work, float* __restrict__ out_pair) {
+    if (threadIdx.x < SPB_PAIR_NOUT) {
+        float v = 0.f;
+        for (int cta = 0; cta < ctas; ++cta) v += work[(size_t)cta * SPB_PAIR_NOUT + threadIdx.x];
+        const float norm = 1.0f / (3.0f * (float)P);
+        out_pair[threadIdx.x] = (threadIdx.x == 15) ? v : v * norm;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch helpers (C ABI)
+// ------------------------------------------------------------------------------------------------
+static inline int ctas_for(int n_tiles, int n_pairs) {
+    int want = (n_tiles + SPB_WARPS - 1) / SPB_WARPS;               // one tile per warp
+    int cap = (148 * 8) / (n_pairs > 0 ? n_pairs : 1);              // ~4 waves of 2 CTAs/SM in total
+    if (cap < 1) cap = 1;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return want;
+}
+
+static inline int ctas_for_points(int P) {
+    int want = (P + SPB_THREADS * 4 - 1) / (SPB_THREADS * 4);
+    if (want > 148 * 4) want = 148 * 4;
+    if (want < 1) want = 1;
+    return want;
+}
+
+extern "C" int64_t spb_workspace_floats(const SpbGeom* geom, int B, int gn) {
+    const int ctas = ctas_for(geom->n_tiles, B);
+    const int nacc = gn ? Sizes<MODE_GN, 8>::NACC : SPB_PAIR_NOUT;
+    const int nseg = gn ? Sizes<MODE_GN, 8>::NSEG : 1;
+    return (int64_t)B * ((int64_t)ctas * nacc + (int64_t)geom->n_tiles * nseg);
+}
+
+extern "C" int64_t spb_workspace_floats_points(int P) { return (int64_t)ctas_for_points(P) * SPB_PAIR_NOUT; }
+
+extern "C" int spb_cost_grad(const SpbGeom* geom, const SpbPair* pairs, int B, float* work, float* out_pair,
+                             float* out_gk, const SpbStats* stats, void* stream) {
+    if (!geom || !pairs || B < 1 || !work || !out_pair || !out_gk) return SPB_EINVAL;
+    if (B > 16) return SPB_ELIMIT;
+    if (geom->n_pts <= 0 || geom->n_tiles <= 0) return SPB_EINVAL;
+    for (int j = 0; j < B; ++j)
+        if (pairs[j].Wl < 2 || pairs[j].Hl < 2 || !pairs[j].trg_rgba || !pairs[j].src_rgb || !pairs[j].pose ||
+            !pairs[j].k || !pairs[j].K_trg)
+            return SPB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    PairPack pack;
+    for (int j = 0; j < B; ++j) pack.p[j] = pairs[j];
+    for (int j = B; j < 16; ++j) pack.p[j] = pairs[0];
+    const int ctas = ctas_for(geom->n_tiles, B);
+    dim3 grid(ctas, B);
+    if (stats) {
+        k_align_inline<MODE_GRAD, 6, true><<<grid, SPB_THREADS, 0, st>>>(*geom, pack, 0.f, work, *stats);
+    } else {
+        SpbStats none = {};
+        k_align_inline<MODE_GRAD, 6, false><<<grid, SPB_THREADS, 0, st>>>(*geom, pack, 0.f, work, none);
+    }
+    SPB_CHECK_LAUNCH();
+    k_finalize_grad<<<B, 128, 0, st>>>(*geom, ctas, work, out_pair, out_gk);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+extern "C" int spb_cost_grad_points(const float* src_pts, const float* src_px, const uint8_t* src_ok, int P, int H,
+                                    int W, const SpbPair* pair, float* work, float* out_pair, void* stream) {
+    if (!src_pts || !src_px || !src_ok || P < 1 || !pair || !work || !out_pair) return SPB_EINVAL;
+    if (pair->Wl < 2 || pair->Hl < 2 || !pair->trg_rgba || !pair->pose || !pair->K_trg) return SPB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = ctas_for_points(P);
+    k_align_points<<<ctas, SPB_THREADS, 0, st>>>(src_pts, src_px, src_ok, P, H, W, *pair, work);
+    SPB_CHECK_LAUNCH();
+    k_finalize_points<<<1, 32, 0, st>>>(ctas, P, work, out_pair);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+extern "C" int spb_gn_ctas(int max_tiles, int n_pairs) { return ctas_for(max_tiles, n_pairs); }
+
+extern "C" int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, int n_pairs,
+                                 int max_tiles, float irls_eps, int with_affine, float* work, int64_t work_stride,
+                                 float* out_pair, float* out_seg, void* stream) {
+    if (!geoms || !pairs || !seg_off || n_pairs < 1 || max_tiles < 1 || !work || !out_pair || !out_seg)
+        return SPB_EINVAL;
+    if (n_pairs > 65535) return SPB_ELIMIT;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = ctas_for(max_tiles, n_pairs);
+    const int nacc = with_affine ? Sizes<MODE_GN, 8>::NACC : Sizes<MODE_GN, 6>::NACC;
+    const int nseg = with_affine ? Sizes<MODE_GN, 8>::NSEG : Sizes<MODE_GN, 6>::NSEG;
+    if (work_stride < (int64_t)ctas * nacc + (int64_t)max_tiles * nseg) return SPB_EINVAL;
+    dim3 grid(ctas, n_pairs);
+    if (with_affine) {
+        k_align_global<MODE_GN, 8><<<grid, SPB_THREADS, 0, st>>>(geoms, pairs, irls_eps, work, work_stride);
+        SPB_CHECK_LAUNCH();
+        k_finalize_gn<8><<<n_pairs, 128, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
+    } else {
+        k_align_global<MODE_GN, 6><<<grid, SPB_THREADS, 0, st>>>(geoms, pairs, irls_eps, work, work_stride);
+        SPB_CHECK_LAUNCH();
+        k_finalize_gn<6><<<n_pairs, 128, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
+    }
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+// gradient mode over device-resident descriptors (batched Adam-parity iterations / benchmark)
+__global__ void k_finalize_grad_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
+                                       const int32_t* __restrict__ seg_off, int ctas, const float* __restrict__ work,
+                                       int64_t work_stride, float* __restrict__ out_pair, float* __restrict__ out_gk) {
+    const int pair = blockIdx.x;
+    const SpbGeom& g = geoms[pairs[pair].geom];
+    const float* pp = work + pair * work_stride;
+    const float* ps = pp + (size_t)ctas * SPB_PAIR_NOUT;
+    const float norm = 1.0f / (3.0f * (float)g.n_pts);
+    if (threadIdx.x < SPB_PAIR_NOUT) {
+        float v = 0.f;
+        for (int cta = 0; cta < ctas; ++cta) v += pp[(size_t)cta * SPB_PAIR_NOUT + threadIdx.x];
+        out_pair[pair * SPB_PAIR_NOUT + threadIdx.x] = (threadIdx.x == 15) ? v : v * norm;
+    }
+    const int so = seg_off[pair];
+    for (int b = threadIdx.x; b < g.n_seg; b += blockDim.x) {
+        float v = 0.f;
+        const int t1 = g.seg_tile[b + 1];
+        for (int t = g.seg_tile[b]; t < t1; ++t) v += ps[t];
+        out_gk[so + b] = v * norm;
+    }
+}
+
+extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, int n_pairs,
+                                   int max_tiles, float* work, int64_t work_stride, float* out_pair, float* out_gk,
+                                   void* stream) {
+    if (!geoms || !pairs || !seg_off || n_pairs < 1 || max_tiles < 1 || !work || !out_pair || !out_gk)
+        return SPB_EINVAL;
+    if (n_pairs > 65535) return SPB_ELIMIT;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = ctas_for(max_tiles, n_pairs);
+    if (work_stride < (int64_t)ctas * SPB_PAIR_NOUT + max_tiles) return SPB_EINVAL;
+    dim3 grid(ctas, n_pairs);
+    k_align_global<MODE_GRAD, 6><<<grid, SPB_THREADS, 0, st>>>(geoms, pairs, 0.f, work, work_stride);
+    SPB_CHECK_LAUNCH();
+    k_finalize_grad_global<<<n_pairs, 128, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_gk);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}

@@ -1,0 +1,341 @@
+// Geometry-side kernels: mask compaction, image packing, source sampling, dense depth expand,
+// point lifting, depth splat.  All once-per-keyframe / once-per-frame work (not per iteration),
+// all HBM-streaming; grids are sized from the data, loads are coalesced along image rows.
+#include "spb_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// compaction pass 1: one warp per (segment,row): popcount of the row
+// ------------------------------------------------------------------------------------------------
+__global__ void k_row_count(const uint8_t* __restrict__ masks, int rows, int W, int32_t* __restrict__ row_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const uint8_t* m = masks + (size_t)row * W;
+    int n = 0;
+    for (int x = lane; x < W; x += 32) n += (m[x] != 0);
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) row_cnt[row] = n;
+}
+
+// pass 2: single-CTA scan over N*H row counts with per-segment padding to SPB_PAD
+__global__ void k_row_scan(const int32_t* __restrict__ row_cnt, int N, int H, int32_t* __restrict__ row_off,
+                           int32_t* __restrict__ seg_ptr, int32_t* __restrict__ seg_ptr_pad,
+                           int32_t* __restrict__ totals) {
+    // phase A: per-segment totals (thread per segment, strided)
+    extern __shared__ int32_t s_seg[];       // [N] counts -> padded starts
+    for (int b = threadIdx.x; b < N; b += blockDim.x) {
+        int n = 0;
+        const int32_t* r = row_cnt + (size_t)b * H;
+        for (int y = 0; y < H; ++y) n += r[y];
+        s_seg[b] = n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0, run_pad = 0;
+        for (int b = 0; b < N; ++b) {
+            const int n = s_seg[b];
+            seg_ptr[b] = run;
+            seg_ptr_pad[b] = run_pad;
+            s_seg[b] = run_pad;
+            run += n;
+            run_pad += (n + SPB_PAD - 1) / SPB_PAD * SPB_PAD;
+        }
+        seg_ptr[N] = run;
+        seg_ptr_pad[N] = run_pad;
+        totals[0] = run;
+        totals[1] = run_pad;
+    }
+    __syncthreads();
+    // phase B: row offsets inside each segment
+    for (int b = threadIdx.x; b < N; b += blockDim.x) {
+        int off = s_seg[b];
+        const int32_t* r = row_cnt + (size_t)b * H;
+        int32_t* o = row_off + (size_t)b * H;
+        for (int y = 0; y < H; ++y) {
+            o[y] = off;
+            off += r[y];
+        }
+    }
+}
+
+// pass 3: ordered scatter, one warp per (segment,row)
+__global__ void k_row_fill(const uint8_t* __restrict__ masks, const float* __restrict__ logd, int64_t seg_stride,
+                           const float* __restrict__ K, int N, int H, int W, const int32_t* __restrict__ row_off,
+                           uint32_t* __restrict__ uv, float* __restrict__ L) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= N * H) return;
+    const int b = row / H, y = row - b * H;
+    const uint8_t* m = masks + (size_t)row * W;
+    const float* lrow = logd + (size_t)b * seg_stride + (size_t)y * W;
+    // static source validity of the point's own pixel (core/dense_optim.py:128-130 on the
+    // re-projected source point): |2 u inv - 1| <= 0.99 on both axes
+    const float tiw = 2.0f * (1.0f / (float)(W - 1));
+    const float tih = 2.0f * (1.0f / (float)(H - 1));
+    const bool yok = fabsf(fmaf((float)y, tih, -1.0f)) <= 0.99f;
+    int off = row_off[row];
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        const bool on = (x < W) && (m[x] != 0);
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (on) {
+            const int dst = off + __popc(bal & ((1u << lane) - 1u));
+            const bool ok = yok && (fabsf(fmaf((float)x, tiw, -1.0f)) <= 0.99f);
+            uv[dst] = (uint32_t)x | ((uint32_t)y << 16) | (ok ? 0x80000000u : 0u);
+            L[dst] = lrow[x];
+        }
+        off += __popc(bal);
+    }
+}
+
+// keypoint pixel (round half even) and log-depth at the keypoint, core/dense_optim.py:51-64
+__global__ void k_keypoints(const float* __restrict__ keypoints, const float* __restrict__ logd, int64_t seg_stride,
+                            int N, int H, int W, float* __restrict__ seg_lkp, int32_t* __restrict__ kp_rc) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= N) return;
+    // 0.5 * (dims - 1) * (x_norm + 1), round, long   (tool/point_utils.py:37-40)
+    const float hr = 0.5f * ((float)H - 1.0f), hc = 0.5f * ((float)W - 1.0f);
+    int r = (int)rintf(hr * (keypoints[2 * b] + 1.0f));
+    int cc = (int)rintf(hc * (keypoints[2 * b + 1] + 1.0f));
+    // python negative indices wrap; anything else out of range is a caller bug -> clamp defensively
+    if (r < 0) r += H;
+    if (cc < 0) cc += W;
+    r = min(max(r, 0), H - 1);
+    cc = min(max(cc, 0), W - 1);
+    kp_rc[2 * b] = r;
+    kp_rc[2 * b + 1] = cc;
+    seg_lkp[b] = logd[(size_t)b * seg_stride + (size_t)r * W + cc];
+}
+
+extern "C" int spb_compact_count(const uint8_t* masks, int N, int H, int W, int32_t* row_cnt, void* stream) {
+    if (!masks || !row_cnt || N < 1 || H < 2 || W < 2 || H > 32767 || W > 65535) return SPB_EINVAL;
+    const int rows = N * H;
+    k_row_count<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(masks, rows, W, row_cnt);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+extern "C" int spb_compact_scan(const int32_t* row_cnt, int N, int H, int32_t* row_off, int32_t* seg_ptr,
+                                int32_t* seg_ptr_pad, int32_t* totals, void* stream) {
+    if (!row_cnt || !row_off || !seg_ptr || !seg_ptr_pad || !totals || N < 1 || H < 1) return SPB_EINVAL;
+    if ((size_t)N * sizeof(int32_t) > 48 * 1024) return SPB_ELIMIT;
+    k_row_scan<<<1, 512, N * sizeof(int32_t), (cudaStream_t)stream>>>(row_cnt, N, H, row_off, seg_ptr, seg_ptr_pad,
+                                                                      totals);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+extern "C" int spb_compact_fill(const uint8_t* masks, const float* logd, int64_t logd_seg_stride,
+                                const float* keypoints, const float* K, int N, int H, int W, const int32_t* row_off,
+                                const int32_t* seg_ptr_pad, uint32_t* uv, float* L, float* seg_lkp, int32_t* kp_rc,
+                                void* stream) {
+    if (!masks || !logd || !keypoints || !row_off || !uv || !L || !seg_lkp || !kp_rc) return SPB_EINVAL;
+    (void)seg_ptr_pad;
+    (void)K;
+    const int rows = N * H;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_row_fill<<<(rows + 7) / 8, 256, 0, st>>>(masks, logd, logd_seg_stride, K, N, H, W, row_off, uv, L);
+    SPB_CHECK_LAUNCH();
+    k_keypoints<<<(N + 127) / 128, 128, 0, st>>>(keypoints, logd, logd_seg_stride, N, H, W, seg_lkp, kp_rc);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// planar (3,H,W) -> RGBA interleaved
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_rgba(const float* __restrict__ planar, int64_t img_stride, int HW, float4* __restrict__ rgba) {
+    const int img = blockIdx.y;
+    const float* p = planar + (size_t)img * img_stride;
+    float4* o = rgba + (size_t)img * HW;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+        o[i] = make_float4(p[i], p[(size_t)HW + i], p[2 * (size_t)HW + i], 0.f);
+}
+
+extern "C" int spb_pack_rgba(const float* planar, int64_t img_stride, int n_img, int Hl, int Wl, float* rgba,
+                             void* stream) {
+    if (!planar || !rgba || n_img < 1 || Hl < 1 || Wl < 1) return SPB_EINVAL;
+    const int HW = Hl * Wl;
+    int bx = (HW + 255) / 256;
+    if (bx > 148 * 8) bx = 148 * 8;
+    k_pack_rgba<<<dim3(bx, n_img), 256, 0, (cudaStream_t)stream>>>(planar, img_stride, HW,
+                                                                  reinterpret_cast<float4*>(rgba));
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cached source samples at a pyramid level: bilinear of the source level image at the point's own
+// pixel scaled to the level (reference re-projects the unprojected point, which returns its own
+// pixel up to float rounding; core/dense_optim.py:315-317)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sample_source(const __grid_constant__ SpbGeom g, const float* __restrict__ img, int Hl, int Wl,
+                                float* __restrict__ out) {
+    const float tiw = 2.0f * (1.0f / (float)(g.W - 1));
+    const float tih = 2.0f * (1.0f / (float)(g.H - 1));
+    const float sx = 0.5f * (float)(Wl - 1), sy = 0.5f * (float)(Hl - 1);
+    const size_t HW = (size_t)Hl * Wl;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pad; p += gridDim.x * blockDim.x) {
+        const uint32_t w = g.uv[p];
+        const float u = (float)(w & 0xffffu), v = (float)((w >> 16) & 0x7fffu);
+        const float ix = (fmaf(u, tiw, -1.0f) + 1.0f) * sx;
+        const float iy = (fmaf(v, tih, -1.0f) + 1.0f) * sy;
+        const float fxf = floorf(ix), fyf = floorf(iy);
+        const int x0 = (int)fxf, y0 = (int)fyf;
+        const float fx = ix - fxf, fy = iy - fyf;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* pl = img + ch * HW;
+            auto tap = [&](int x, int y) -> float {
+                return (x < 0 || y < 0 || x >= Wl || y >= Hl) ? 0.f : pl[(size_t)y * Wl + x];
+            };
+            float val, d0, d1;
+            blend(tap(x0, y0), tap(x0 + 1, y0), tap(x0, y0 + 1), tap(x0 + 1, y0 + 1), fx, fy, val, d0, d1);
+            out[(size_t)ch * g.n_pad + p] = val;
+        }
+    }
+}
+
+extern "C" int spb_sample_source(const SpbGeom* geom, const float* src_planar, int Hl, int Wl, float* out,
+                                 void* stream) {
+    if (!geom || !src_planar || !out || Hl < 1 || Wl < 1 || geom->n_pad < 1) return SPB_EINVAL;
+    int bx = (geom->n_pad + 255) / 256;
+    if (bx > 148 * 8) bx = 148 * 8;
+    k_sample_source<<<bx, 256, 0, (cudaStream_t)stream>>>(*geom, src_planar, Hl, Wl, out);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// unproject_kf_to_depths: dense exp((L + shift_b) * mask)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_dense_depths(const uint8_t* __restrict__ masks, const float* __restrict__ logd, int64_t seg_stride,
+                               const float* __restrict__ seg_lkp, const float* __restrict__ k, int HW,
+                               float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const float shift = k[b] - seg_lkp[b];
+    const uint8_t* m = masks + (size_t)b * HW;
+    const float* l = logd + (size_t)b * seg_stride;
+    float* o = out + (size_t)b * HW;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+        o[i] = expf((l[i] + shift) * (m[i] ? 1.0f : 0.0f));
+}
+
+extern "C" int spb_dense_depths(const uint8_t* masks, const float* logd, int64_t logd_seg_stride,
+                                const float* seg_lkp, const float* k, int N, int H, int W, float* out, void* stream) {
+    if (!masks || !logd || !seg_lkp || !k || !out || N < 1 || N > 65535) return SPB_EINVAL;
+    const int HW = H * W;
+    int bx = (HW + 255) / 256;
+    if (bx > 1024) bx = 1024;
+    k_dense_depths<<<dim3(bx, N), 256, 0, (cudaStream_t)stream>>>(masks, logd, logd_seg_stride, seg_lkp, k, HW, out);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifted points (unproject_kf) and the depth splat (estimate_depth_kf_native)
+// ------------------------------------------------------------------------------------------------
+template <bool SPLAT>
+__global__ void k_lift(const __grid_constant__ SpbGeom g, const float* __restrict__ k, const float* __restrict__ pose,
+                       float* __restrict__ src_pts, int64_t* __restrict__ seg_ids, uint8_t* __restrict__ src_ok,
+                       int mean, unsigned long long* __restrict__ keys, float* __restrict__ sum) {
+    const int lane = threadIdx.x & 31;
+    const int wglobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int wstride = gridDim.x * (blockDim.x >> 5);
+    const float ifx = 1.0f / g.K[0], ify = 1.0f / g.K[4], cx = g.K[2], cy = g.K[5];
+    const float fx = g.K[0], fy = g.K[4];
+    float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tt[3] = {0, 0, 0};
+    if (SPLAT && pose != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            R[3 * i] = pose[4 * i]; R[3 * i + 1] = pose[4 * i + 1]; R[3 * i + 2] = pose[4 * i + 2];
+            tt[i] = pose[4 * i + 3];
+        }
+    }
+    const int4* tiles = reinterpret_cast<const int4*>(g.tiles);
+    for (int t = wglobal; t < g.n_tiles; t += wstride) {
+        const int4 td = tiles[t];
+        const float shift = k[td.x] - g.seg_lkp[td.x];
+        for (int i = lane; i < td.z; i += 32) {
+            const int p = td.y + i, q = td.w + i;
+            const uint32_t w = g.uv[p];
+            const float u = (float)(w & 0xffffu), v = (float)((w >> 16) & 0x7fffu);
+            const float z = expf(g.logd[p] + shift);
+            const float Xx = (u - cx) * z * ifx, Xy = (v - cy) * z * ify;
+            if (!SPLAT) {
+                if (src_pts) { src_pts[3 * (size_t)q] = Xx; src_pts[3 * (size_t)q + 1] = Xy; src_pts[3 * (size_t)q + 2] = z; }
+                if (seg_ids) seg_ids[q] = td.x;
+                if (src_ok) src_ok[q] = ((w >> 31) && z > 1e-7f) ? 1 : 0;
+            } else {
+                const float Yx = fmaf(R[0], Xx, fmaf(R[1], Xy, R[2] * z)) + tt[0];
+                const float Yy = fmaf(R[3], Xx, fmaf(R[4], Xy, R[5] * z)) + tt[1];
+                const float Yz = fmaf(R[6], Xx, fmaf(R[7], Xy, R[8] * z)) + tt[2];
+                const float zi = fabsf(Yz) > 1e-6f ? 1.0f / Yz : 1e-6f;
+                const float up = fmaf(Yx * fx, zi, cx), vp = fmaf(Yy * fy, zi, cy);
+                // .long() truncates toward zero (core/ops.py:66); keep NaN/inf out
+                if (!(Yz > 1e-6f) || !isfinite(up) || !isfinite(vp)) continue;
+                if (fabsf(up) > 1e6f || fabsf(vp) > 1e6f) continue;
+                const int col = (int)up, row = (int)vp;
+                if (row < 0 || row >= g.H || col < 0 || col >= g.W) continue;
+                const int idx = row * g.W + col;
+                if (mean) {
+                    atomicAdd(sum + idx, Yz);
+                    atomicAdd(keys + idx, 1ull);
+                } else {
+                    // last writer in point order wins == CPU scatter_ semantics
+                    const unsigned long long key = ((unsigned long long)(q + 1) << 32) | __float_as_uint(Yz);
+                    atomicMax(keys + idx, key);
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_splat_resolve(const unsigned long long* __restrict__ keys, const float* __restrict__ sum, int mean,
+                                int HW, float* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[i];
+        if (mean)   // scatter_reduce_('mean') with include_self=True: (0 + sum) / (count + 1)
+            out[i] = key ? sum[i] / (float)(key + 1ull) : 0.0f;
+        else
+            out[i] = key ? __uint_as_float((unsigned)(key & 0xffffffffull)) : 0.0f;
+    }
+}
+
+static inline int lift_blocks(int n_tiles) {
+    int bx = (n_tiles + 7) / 8;
+    if (bx > 148 * 8) bx = 148 * 8;
+    return bx < 1 ? 1 : bx;
+}
+
+extern "C" int spb_lift_points(const SpbGeom* geom, const float* k, float* src_pts, int64_t* seg_ids,
+                               uint8_t* src_ok, void* stream) {
+    if (!geom || !k || geom->n_tiles < 1) return SPB_EINVAL;
+    k_lift<false><<<lift_blocks(geom->n_tiles), 256, 0, (cudaStream_t)stream>>>(*geom, k, nullptr, src_pts, seg_ids,
+                                                                               src_ok, 0, nullptr, nullptr);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+extern "C" int spb_depth_splat(const SpbGeom* geom, const float* k, const float* pose, int mean,
+                               unsigned long long* keys, float* sum, float* out, void* stream) {
+    if (!geom || !k || !keys || !out || geom->n_tiles < 1) return SPB_EINVAL;
+    if (mean && !sum) return SPB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = geom->H * geom->W;
+    cudaError_t e = cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)HW, st);
+    if (e != cudaSuccess) return (int)e;
+    if (mean) {
+        e = cudaMemsetAsync(sum, 0, sizeof(float) * (size_t)HW, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    k_lift<true><<<lift_blocks(geom->n_tiles), 256, 0, st>>>(*geom, k, pose, nullptr, nullptr, nullptr, mean, keys, sum);
+    SPB_CHECK_LAUNCH();
+    int bx = (HW + 255) / 256;
+    if (bx > 148 * 8) bx = 148 * 8;
+    k_splat_resolve<<<bx, 256, 0, st>>>(keys, sum, mean, HW, out);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+extern "C" int spb_version(void) { return 100; }

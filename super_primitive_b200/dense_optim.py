@@ -1,0 +1,415 @@
+"""Drop-in replacement for the reference's ``core.dense_optim`` (same callables, same
+positional/keyword signatures, same return dictionaries and AssertionError convention), backed
+by the hand-written sm_100a kernels behind the C ABI in ``include/spb200.h``.
+
+Reference mapping (paths relative to the reference checkout):
+    photomeric_cost              core/dense_optim.py:265-363
+    photomeric_cost_precomputed  core/dense_optim.py:365-403
+    unproject_kf                 core/dense_optim.py:176-200
+    unproject_kf_to_depths       core/dense_optim.py:164-174
+    transform_points             core/dense_optim.py:117-122
+    project_points               core/ops.py:42-43 (re-exported by core/dense_optim.py:7)
+    infer_depth_seeds / expdepth / unproject_segments / get_pixels / img_interp /
+    affine_compensation_batch_v2 / calculate_residual: the intermediate stages of the reference are
+    fused into one kernel here; they are not separately exposed because no caller outside core/
+    uses them.
+
+The forward AND the backward of the reference's autograd graph are computed by one fused kernel
+launch; ``torch.autograd.Function`` only scales the stored gradients by the incoming grad.
+There is no CPU fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as nat
+from .geometry import CompactGeometry, _f32c, _stream, geometry_of, pack_rgba
+from .ops import project_points, transform_points  # noqa: F401  (re-exported like the reference)
+
+CHECK_FINITE_DEFAULT = True
+
+
+# ------------------------------------------------------------------------------------------------
+# lazily materialised statistics dictionary
+# ------------------------------------------------------------------------------------------------
+class LazyResult(dict):
+    """``{'residual': ...}`` plus per-point statistics that are only computed when somebody
+    looks at them (the callers always request collect_stats=2 but only the GUI reads them)."""
+
+    def __init__(self, residual, producer=None):
+        super().__init__(residual=residual)
+        self._producer = producer
+
+    def _fill(self):
+        if self._producer is not None:
+            prod, self._producer = self._producer, None
+            super().update(prod())
+
+    def __getitem__(self, key):
+        if key != 'residual':
+            self._fill()
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        if key != 'residual':
+            self._fill()
+        return super().get(key, default)
+
+    def __contains__(self, key):
+        if key != 'residual':
+            self._fill()
+        return super().__contains__(key)
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __len__(self):
+        self._fill()
+        return super().__len__()
+
+    def keys(self):
+        self._fill()
+        return super().keys()
+
+    def items(self):
+        self._fill()
+        return super().items()
+
+    def values(self):
+        self._fill()
+        return super().values()
+
+    def update(self, *a, **kw):
+        self._fill()
+        return super().update(*a, **kw)
+
+    def copy(self):
+        self._fill()
+        return dict(self)
+
+
+# ------------------------------------------------------------------------------------------------
+# shared launch helper: B pairs over one compact geometry
+# ------------------------------------------------------------------------------------------------
+def _launch_pairs(geom: CompactGeometry, src_rgb, trg_rgba, trg_Ks, poses, k, aff_src, aff_trg, tau,
+                  stats=None):
+    """poses (B,4,4), trg_rgba (B,Hl,Wl,4), trg_Ks (B,3,3) or (3,3), aff_trg (B,2)|None.
+    Returns out_pair (B,16), out_gk (B,N)."""
+    lib = nat.lib()
+    B = poses.shape[0]
+    dev = poses.device
+    Hl, Wl = trg_rgba.shape[1], trg_rgba.shape[2]
+    out_pair = torch.empty((B, nat.PAIR_NOUT), dtype=torch.float32, device=dev)
+    out_gk = torch.empty((B, geom.N), dtype=torch.float32, device=dev)
+    done = 0
+    while done < B:
+        nb = min(nat.MAX_INLINE_PAIRS, B - done)
+        pairs = (nat.SpbPair * nb)()
+        for i in range(nb):
+            j = done + i
+            p = pairs[i]
+            p.trg_rgba = trg_rgba[j].data_ptr()
+            p.src_rgb = src_rgb.data_ptr()
+            p.K_trg = (trg_Ks[j] if trg_Ks.dim() == 3 else trg_Ks).data_ptr()
+            p.pose = poses[j].data_ptr()
+            p.k = k.data_ptr()
+            p.aff_src = nat.ptr(aff_src)
+            p.aff_trg = None if aff_trg is None else aff_trg[j].data_ptr()
+            p.geom = 0
+            p.Hl, p.Wl = Hl, Wl
+            p.tau = tau
+        work = torch.empty(lib.spb_workspace_floats(geom.cref, nb, 0), dtype=torch.float32, device=dev)
+        st_ref = None
+        if stats is not None:
+            st_ref = C.byref(stats(done, nb))
+        nat.check(lib.spb_cost_grad(geom.cref, pairs, nb, work.data_ptr(), out_pair[done:].data_ptr(),
+                                    out_gk[done:].data_ptr(), st_ref, _stream()), "spb_cost_grad")
+        done += nb
+    return out_pair, out_gk
+
+
+class _PairCost(torch.autograd.Function):
+    """residual (B,) with gradients to k (N,), poses (B,4,4), aff_src (2,)|(1,2), aff_trg (2,)|(B,2)."""
+
+    @staticmethod
+    def forward(ctx, k, poses, aff_src, aff_trg, geom, src_rgb, trg_rgba, trg_Ks, tau, check):
+        k_c = _f32c(k)
+        poses_c = _f32c(poses)
+        B = poses_c.shape[0]
+        a_s = None if aff_src is None else _f32c(aff_src).reshape(-1)
+        a_t = None if aff_trg is None else _f32c(aff_trg).reshape(-1, 2).expand(B, 2).contiguous()
+        out_pair, out_gk = _launch_pairs(geom, src_rgb, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau)
+        if check:
+            # the reference asserts finiteness at five sites per call (core/dense_optim.py:44,78,311,
+            # 321,340-343); one flag read covers inputs and outputs here
+            if not bool(torch.isfinite(out_pair).all()):
+                raise AssertionError("non-finite photometric cost or gradient (inputs not finite?)")
+        ctx.save_for_backward(out_pair, out_gk)
+        ctx.shapes = (None if aff_src is None else aff_src.shape, None if aff_trg is None else aff_trg.shape,
+                      poses.shape)
+        return out_pair[:, 0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        out_pair, out_gk = ctx.saved_tensors
+        B = out_pair.shape[0]
+        g = g.reshape(B).to(torch.float32)
+        needs = ctx.needs_input_grad
+        g_k = g_pose = g_as = g_at = None
+        if needs[0]:
+            g_k = (g[:, None] * out_gk).sum(0)
+        if needs[1]:
+            g_pose = torch.zeros((B, 4, 4), dtype=torch.float32, device=g.device)
+            g_pose[:, :3, :3] = out_pair[:, 4:13].reshape(B, 3, 3) * g[:, None, None]
+            g_pose[:, :3, 3] = out_pair[:, 1:4] * g[:, None]
+            g_pose = g_pose.reshape(ctx.shapes[2])
+        s_shape, t_shape, _ = ctx.shapes
+        if s_shape is not None and (needs[2] or needs[3]):
+            ga = out_pair[:, 13:15] * g[:, None]
+            if needs[2]:
+                g_as = (-ga.sum(0)).reshape(s_shape)
+            if needs[3]:
+                g_at = ga.sum(0).reshape(t_shape) if len(t_shape) == 1 else ga.reshape(t_shape)
+        return g_k, g_pose, g_as, g_at, None, None, None, None, None, None
+
+
+def _check_cfg(cost_config):
+    mode = cost_config['mode']
+    if mode != 'colour':
+        # the reference's normal/kappa terms are dead code (residual_cosine is never assigned,
+        # core/dense_optim.py:241-261) and every caller forces 'colour'
+        raise NotImplementedError(f"residual mode {mode!r}: only 'colour' is implemented "
+                                  "(the reference never computes the normal term)")
+    return cost_config['collect_stats'], cost_config.get('check_finite', CHECK_FINITE_DEFAULT)
+
+
+def _affine_pair(affine_comp):
+    if affine_comp is None:
+        return None, None
+    a_s, a_t = affine_comp
+    if a_s is None:
+        assert a_t is None
+        return None, None
+    return a_s, a_t
+
+
+# ------------------------------------------------------------------------------------------------
+# statistics (slow path)
+# ------------------------------------------------------------------------------------------------
+def _point_stats(geom, src_image, src_rgb, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau, batch):
+    dev = poses_c.device
+    B, P = poses_c.shape[0], geom.P
+    src_pts = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    moved = torch.empty((B, P, 3), dtype=torch.float32, device=dev)
+    trg_px = torch.empty((B, 3, P), dtype=torch.float32, device=dev)
+    raw = torch.empty((B, 3, P), dtype=torch.float32, device=dev)
+    trg_ok = torch.empty((B, P), dtype=torch.uint8, device=dev)
+    full = torch.empty((B, P), dtype=torch.int64, device=dev)
+
+    def make(done, nb):
+        n = P
+        return nat.SpbStats(src_pts.data_ptr(), moved[done:].data_ptr(), trg_px[done:].data_ptr(),
+                            raw[done:].data_ptr(), trg_ok[done:].data_ptr(), None, full[done:].data_ptr(), None)
+
+    _launch_pairs(geom, src_rgb, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau, stats=make)
+    idx = geom.pad_index()
+    src_ok = torch.empty(P, dtype=torch.uint8, device=dev)
+    nat.check(nat.lib().spb_lift_points(geom.cref, k_c.data_ptr(), None, None, src_ok.data_ptr(), _stream()),
+              "spb_lift_points")
+    src_pixels = src_rgb[:, idx][None]
+    return {'segm_ids': geom.seg_ids(),
+            'src_pixels': src_pixels,
+            'src_in_trg_pixels': trg_px,
+            'src_valid_mask': src_ok.bool()[None],
+            'trg_valid_mask': trg_ok.bool(),
+            'full_mask': full[:, None],
+            'src_pts': src_pts,
+            'src_in_trg_pts': moved if batch else moved[0],
+            'residual_raw': raw,
+            'median_depth': None}
+
+
+def _keypoint_stats(geom, k_c, poses_c, trg_Ks, K_proj, tau, batch):
+    """N-sized host-side logic of collect_stats > 1 (core/dense_optim.py:291-308,
+    core/dense_optim_batch.py:83-100): where the segment keypoints land in the target(s)."""
+    H, W = geom.H, geom.W
+    rc = geom.kp_rc.to(torch.float32)
+    K = geom.K
+    z = torch.exp(k_c)
+    X = torch.stack([(rc[:, 1] - K[0, 2]) * z / K[0, 0], (rc[:, 0] - K[1, 2]) * z / K[1, 1], z], 1)
+    Y = torch.einsum('bij,nj->bni', poses_c[:, :3, :3], X) + poses_c[:, None, :3, 3]
+    Kt = trg_Ks if trg_Ks.dim() == 3 else trg_Ks[None]
+    uv = _project(Y, Kt)
+    inv = 1.0 / (torch.tensor([W, H], dtype=torch.float32, device=Y.device) - 1)
+    norm = 2 * uv * inv - 1
+    ok = torch.all(torch.abs(norm) <= 0.99, dim=-1) & (Y[..., 2] > tau)
+    proj = _project(Y, K_proj if K_proj.dim() == 3 else K_proj[None])
+    if batch:
+        return {'src_in_trg_keypoints': proj, 'src_in_trg_keypoints_z': Y[..., 2],
+                'src_in_trg_keypoints_valid_mask': ok}
+    return {'src_in_trg_keypoints': proj[0], 'src_in_trg_keypoints_z': Y[0, :, 2],
+            'src_in_trg_keypoints_valid_mask': ok}
+
+
+def _project(Y, K):
+    eps = 1e-6
+    z = Y[..., 2]
+    zi = torch.where(torch.abs(z) > eps, 1.0 / z, torch.full_like(z, eps))
+    u = Y[..., 0] * K[:, None, 0, 0] * zi + K[:, None, 0, 2]
+    v = Y[..., 1] * K[:, None, 1, 1] * zi + K[:, None, 1, 2]
+    return torch.stack([u, v], -1)
+
+
+# ------------------------------------------------------------------------------------------------
+# public entry points
+# ------------------------------------------------------------------------------------------------
+def photomeric_cost(src_keyframe, trg_keyframe, src_keypoint_logdepth, pose, cost_config, affine_comp=None):
+    """Masked L1 photometric cost of the source segments warped into one target frame.
+    Returns ``{'residual': (1,)}`` (+ statistics when ``collect_stats > 0``)."""
+    collect_stats, check = _check_cfg(cost_config)
+    geom = geometry_of(src_keyframe)
+    src_rgb = geom.source_samples(src_keyframe.image)
+    trg_rgba = pack_rgba(trg_keyframe.image)
+    a_s, a_t = _affine_pair(affine_comp)
+    trg_K = _f32c(trg_keyframe.K)
+    tau = 1e-7
+    residual = _PairCost.apply(src_keypoint_logdepth, pose[None], a_s, a_t, geom, src_rgb, trg_rgba, trg_K, tau,
+                               check)
+    if collect_stats <= 0:
+        return {'residual': residual}
+    # snapshot the small parameters: the optimiser may step before the statistics are read
+    k_c = _f32c(src_keypoint_logdepth).clone()
+    poses_c = _f32c(pose)[None].clone()
+    as_c = None if a_s is None else _f32c(a_s).reshape(-1).clone()
+    at_c = None if a_t is None else _f32c(a_t).reshape(1, 2).clone()
+    K_img = _f32c(trg_keyframe.K_img)
+    src_image = src_keyframe.image
+
+    def produce():
+        with torch.no_grad():
+            out = _point_stats(geom, src_image, src_rgb, trg_rgba, trg_K, poses_c, k_c, as_c, at_c, tau, False)
+            if collect_stats > 1:
+                out.update(_keypoint_stats(geom, k_c, poses_c, trg_K, K_img, tau, False))
+        return out
+
+    res = LazyResult(residual, produce)
+    if cost_config.get('eager_stats', False):
+        res._fill()
+    return res
+
+
+def unproject_kf_to_depths(kf, keypoint_logdepth):
+    """Dense (N,H,W) per-segment depth, 1 outside the masks (core/dense_optim.py:164-174).
+    Differentiable w.r.t. ``keypoint_logdepth`` like the reference."""
+    geom = geometry_of(kf)
+    return _DenseDepths.apply(keypoint_logdepth, kf.keypoint_regions, kf.get_logdepth(), geom)
+
+
+class _DenseDepths(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, k, regions, logd, geom):
+        if not bool(torch.isfinite(k).all()):
+            raise AssertionError("keypoint_logdepth is not finite")
+        k_c = _f32c(k)
+        masks = regions.detach()
+        if masks.dtype != torch.bool:
+            masks = masks != 0
+        m8 = masks.contiguous().view(torch.uint8)
+        ld = _f32c(logd)
+        N, H, W = m8.shape
+        out = torch.empty((N, H, W), dtype=torch.float32, device=k_c.device)
+        nat.check(nat.lib().spb_dense_depths(m8.data_ptr(), ld.data_ptr(), H * W if ld.dim() == 3 else 0,
+                                             geom.seg_lkp.data_ptr(), k_c.data_ptr(), N, H, W, out.data_ptr(),
+                                             _stream()), "spb_dense_depths")
+        ctx.save_for_backward(out, m8)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out, m8 = ctx.saved_tensors
+        return (g * out * m8).sum((1, 2)), None, None, None
+
+
+def unproject_kf(kf, keypoint_logdepth, jacobian=False):
+    """Lift a keyframe's segments to 3-D points + sample its own image (core/dense_optim.py:176-200).
+    The returned dict is what ``photomeric_cost_precomputed`` consumes."""
+    geom = geometry_of(kf)
+    if not bool(torch.isfinite(keypoint_logdepth).all()):
+        raise AssertionError("keypoint_logdepth is not finite")
+    k_c = _f32c(keypoint_logdepth)
+    dev = k_c.device
+    P = geom.P
+    src_pts = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    seg_ids = torch.empty(P, dtype=torch.int64, device=dev)
+    src_ok = torch.empty(P, dtype=torch.uint8, device=dev)
+    nat.check(nat.lib().spb_lift_points(geom.cref, k_c.data_ptr(), src_pts.data_ptr(), seg_ids.data_ptr(),
+                                        src_ok.data_ptr(), _stream()), "spb_lift_points")
+    src_rgb = geom.source_samples(kf.image)
+    src_pixels = src_rgb[:, geom.pad_index()][None].contiguous()
+    return {'src_pixels': src_pixels,
+            'src_valid_mask': src_ok.bool()[None],
+            'src_pts': src_pts,
+            'segm_ids': seg_ids,
+            'spatial_size': kf.geo_spatial_dim()}
+
+
+class _PointsCost(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pose, aff_src, aff_trg, src_pts, src_px, src_ok, dims, trg_rgba, trg_K, check):
+        lib = nat.lib()
+        pose_c = _f32c(pose)
+        a_s = None if aff_src is None else _f32c(aff_src).reshape(-1)
+        a_t = None if aff_trg is None else _f32c(aff_trg).reshape(-1)
+        P = src_pts.shape[0]
+        dev = pose_c.device
+        pr = nat.SpbPair(trg_rgba.data_ptr(), None, trg_K.data_ptr(), pose_c.data_ptr(), None, nat.ptr(a_s),
+                         nat.ptr(a_t), 0, trg_rgba.shape[1], trg_rgba.shape[2], 1e-7)
+        work = torch.empty(lib.spb_workspace_floats_points(P), dtype=torch.float32, device=dev)
+        out_pair = torch.empty(nat.PAIR_NOUT, dtype=torch.float32, device=dev)
+        nat.check(lib.spb_cost_grad_points(src_pts.data_ptr(), src_px.data_ptr(), src_ok.data_ptr(), P,
+                                           int(dims[0]), int(dims[1]), C.byref(pr), work.data_ptr(),
+                                           out_pair.data_ptr(), _stream()), "spb_cost_grad_points")
+        if check and not bool(torch.isfinite(out_pair).all()):
+            raise AssertionError("non-finite photometric cost or gradient")
+        ctx.save_for_backward(out_pair)
+        ctx.shapes = (None if aff_src is None else aff_src.shape, None if aff_trg is None else aff_trg.shape)
+        return out_pair[0:1].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (out_pair,) = ctx.saved_tensors
+        g = g.reshape(()).to(torch.float32)
+        needs = ctx.needs_input_grad
+        g_pose = g_as = g_at = None
+        if needs[0]:
+            g_pose = torch.zeros((4, 4), dtype=torch.float32, device=g.device)
+            g_pose[:3, :3] = out_pair[4:13].reshape(3, 3) * g
+            g_pose[:3, 3] = out_pair[1:4] * g
+        if ctx.shapes[0] is not None:
+            ga = out_pair[13:15] * g
+            if needs[1]:
+                g_as = (-ga).reshape(ctx.shapes[0])
+            if needs[2]:
+                g_at = ga.reshape(ctx.shapes[1])
+        return g_pose, g_as, g_at, None, None, None, None, None, None, None
+
+
+def photomeric_cost_precomputed(src_precomputed, trg_keyframe, pose, cost_config, affine_comp=None):
+    """Tracking cost against pre-lifted source points (core/dense_optim.py:365-403): only the pose
+    and the affine terms receive gradients."""
+    _, check = _check_cfg(cost_config)
+    src_pts = _f32c(src_precomputed['src_pts'])
+    P = src_pts.shape[0]
+    src_px = _f32c(src_precomputed['src_pixels'])[0, :3].contiguous()
+    src_ok = src_precomputed['src_valid_mask'].reshape(-1)
+    src_ok = (src_ok if src_ok.dtype == torch.bool else src_ok != 0).contiguous().view(torch.uint8)
+    if src_px.shape[1] != P or src_ok.shape[0] != P:
+        raise AssertionError("src_precomputed tensors disagree on the number of points")
+    a_s, a_t = _affine_pair(affine_comp)
+    trg_rgba = pack_rgba(trg_keyframe.image)
+    residual = _PointsCost.apply(pose, a_s, a_t, src_pts, src_px, src_ok, tuple(src_precomputed['spatial_size']),
+                                 trg_rgba[0], _f32c(trg_keyframe.K), check)
+    return {'residual': residual}

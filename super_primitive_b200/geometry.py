@@ -1,0 +1,200 @@
+"""Compact per-segment source geometry and its caches (host side of the geometry build).
+
+The reference keeps every keyframe as dense ``(N,H,W)`` tensors and re-derives the point list
+with ``torch.where`` on every cost evaluation (core/dense_optim.py:89-114).  Here the masks are
+compacted ONCE per keyframe into a point list in the same (segment,row,col) order:
+
+    uv      [n_pad] uint32   u | v<<16 | src_ok<<31
+    logd    [n_pad] float32  raw per-segment log-depth at the point
+    tiles   [n_tiles,4] int32  {segment, padded start, count, unpadded start}, <=128 points each
+    seg_lkp [N] float32      log-depth at each segment's keypoint
+
+Every segment's range is padded to a multiple of 4 points (16-byte aligned float/uint32 runs).
+Caches are keyed on tensor identity + in-place version counters and hold weak references only,
+so a caller replacing ``logdepth_perseg`` / ``keypoint_regions`` gets a fresh build.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t):
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class CompactGeometry:
+    """Device-resident compacted geometry of one source keyframe."""
+
+    def __init__(self, regions, logd, keypoints, K):
+        if not regions.is_cuda:
+            raise RuntimeError("super_primitive_b200 runs on CUDA tensors only (no CPU fallback)")
+        lib = nat.lib()
+        dev = regions.device
+        N, H, W = regions.shape
+        if keypoints.shape[0] != N:
+            raise AssertionError("one keypoint per segment expected")
+        per_seg = logd.dim() == 3
+        if per_seg and logd.shape[0] != N:
+            raise AssertionError("logdepth_perseg and keypoint_regions disagree on N")
+        masks = regions.detach()
+        if masks.dtype != torch.bool:
+            masks = masks != 0
+        masks = masks.contiguous()
+        m8 = masks.view(torch.uint8)
+        logd_c = _f32c(logd)
+        kps = _f32c(keypoints)
+        self.K = _f32c(K).clone()
+        st = _stream()
+        i32 = dict(dtype=torch.int32, device=dev)
+        row_cnt = torch.empty(N * H, **i32)
+        row_off = torch.empty(N * H, **i32)
+        seg_ptr = torch.empty(N + 1, **i32)
+        seg_ptr_pad = torch.empty(N + 1, **i32)
+        totals = torch.empty(2, **i32)
+        nat.check(lib.spb_compact_count(m8.data_ptr(), N, H, W, row_cnt.data_ptr(), st), "spb_compact_count")
+        nat.check(lib.spb_compact_scan(row_cnt.data_ptr(), N, H, row_off.data_ptr(), seg_ptr.data_ptr(),
+                                       seg_ptr_pad.data_ptr(), totals.data_ptr(), st), "spb_compact_scan")
+        # one host sync per keyframe: the point count sizes the allocations (the reference syncs on
+        # torch.where every iteration)
+        host = torch.cat([totals, seg_ptr, seg_ptr_pad]).cpu().numpy()
+        P, P_pad = int(host[0]), int(host[1])
+        sp = host[2:2 + N + 1].astype(np.int64)
+        spp = host[2 + N + 1:].astype(np.int64)
+        if P <= 0:
+            raise AssertionError("keyframe has no segment pixels")
+        self.N, self.H, self.W, self.P, self.P_pad = N, H, W, P, P_pad
+        self.uv = torch.zeros(P_pad, dtype=torch.int32, device=dev)      # bit pattern of uint32
+        self.logd = torch.zeros(P_pad, dtype=torch.float32, device=dev)
+        self.seg_lkp = torch.empty(N, dtype=torch.float32, device=dev)
+        self.kp_rc = torch.empty((N, 2), **i32)
+        nat.check(lib.spb_compact_fill(m8.data_ptr(), logd_c.data_ptr(), H * W if per_seg else 0, kps.data_ptr(),
+                                       self.K.data_ptr(), N, H, W, row_off.data_ptr(), seg_ptr_pad.data_ptr(),
+                                       self.uv.data_ptr(), self.logd.data_ptr(), self.seg_lkp.data_ptr(),
+                                       self.kp_rc.data_ptr(), st), "spb_compact_fill")
+        # tile table (host, once): tiles never straddle segments
+        cnt = sp[1:] - sp[:-1]
+        ntile = (cnt + nat.TILE - 1) // nat.TILE
+        seg_tile = np.zeros(N + 1, dtype=np.int64)
+        np.cumsum(ntile, out=seg_tile[1:])
+        T = int(seg_tile[-1])
+        seg_of = np.repeat(np.arange(N), ntile)
+        j = np.arange(T) - seg_tile[seg_of]
+        tiles = np.empty((T, 4), dtype=np.int32)
+        tiles[:, 0] = seg_of
+        tiles[:, 1] = spp[seg_of] + j * nat.TILE
+        tiles[:, 2] = np.minimum(cnt[seg_of] - j * nat.TILE, nat.TILE)
+        tiles[:, 3] = sp[seg_of] + j * nat.TILE
+        self.n_tiles = T
+        self.tiles = torch.from_numpy(tiles).to(dev)
+        self.seg_tile = torch.from_numpy(seg_tile.astype(np.int32)).to(dev)
+        self.seg_ptr_host = sp
+        self.seg_ptr_pad_host = spp
+        self._pad_index = None
+        self._seg_ids = None
+        self.c = nat.SpbGeom(self.uv.data_ptr(), self.logd.data_ptr(), self.tiles.data_ptr(),
+                             self.seg_tile.data_ptr(), self.seg_lkp.data_ptr(), self.K.data_ptr(),
+                             P, P_pad, N, T, H, W)
+        self.cref = C.byref(self.c)
+        self._levels = OrderedDict()     # source-sample caches per (image identity)
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def pad_index(self):
+        """(P,) int64: position of every unpadded point in the padded arrays."""
+        if self._pad_index is None:
+            cnt = self.seg_ptr_host[1:] - self.seg_ptr_host[:-1]
+            seg = np.repeat(np.arange(self.N), cnt)
+            idx = np.arange(self.P) + (self.seg_ptr_pad_host[:-1] - self.seg_ptr_host[:-1])[seg]
+            self._pad_index = torch.from_numpy(idx).to(self.uv.device)
+            self._seg_ids = torch.from_numpy(seg.astype(np.int64)).to(self.uv.device)
+        return self._pad_index
+
+    def seg_ids(self):
+        self.pad_index()
+        return self._seg_ids
+
+    def source_samples(self, image):
+        """[3][n_pad] bilinear samples of the source level image at every point's own pixel
+        (cached per image tensor)."""
+        key = (id(image), image._version, tuple(image.shape))
+        hit = self._levels.get(key)
+        if hit is not None and hit[0]() is image:
+            self._levels.move_to_end(key)
+            return hit[1]
+        img = _f32c(image[:3])
+        out = torch.empty((3, self.P_pad), dtype=torch.float32, device=img.device)
+        nat.check(nat.lib().spb_sample_source(self.cref, img.data_ptr(), img.shape[1], img.shape[2],
+                                              out.data_ptr(), _stream()), "spb_sample_source")
+        self._levels[key] = (weakref.ref(image), out)
+        while len(self._levels) > 8:
+            self._levels.popitem(last=False)
+        return out
+
+    def bytes(self):
+        return self.P_pad * 8 + self.n_tiles * 16 + self.N * 8
+
+
+# ---------------------------------------------------------------------------------------------------
+_GEOM_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_RGBA_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+GEOM_CACHE_SIZE = 16
+RGBA_CACHE_SIZE = 32
+
+
+def geometry_of(kf) -> CompactGeometry:
+    """Compact geometry of a keyframe, cached on the identity/version of its geometry tensors."""
+    reg, ld, kp, K = kf.keypoint_regions, kf.get_logdepth(), kf.keypoints, kf.K
+    key = (id(reg), reg._version, id(ld), ld._version, id(kp), kp._version, id(K), K._version)
+    hit = _GEOM_CACHE.get(key)
+    if hit is not None and hit[0]() is reg and hit[1]() is ld and hit[2]() is kp and hit[3]() is K:
+        _GEOM_CACHE.move_to_end(key)
+        return hit[4]
+    g = CompactGeometry(reg, ld, kp, K)
+    _GEOM_CACHE[key] = (weakref.ref(reg), weakref.ref(ld), weakref.ref(kp), weakref.ref(K), g)
+    while len(_GEOM_CACHE) > GEOM_CACHE_SIZE:
+        _GEOM_CACHE.popitem(last=False)
+    return g
+
+
+def pack_rgba(images):
+    """(3,Hl,Wl) or (B,>=3,Hl,Wl) planar float -> (B,Hl,Wl,4) RGBA-interleaved, cached per tensor."""
+    key = (id(images), images._version, tuple(images.shape))
+    hit = _RGBA_CACHE.get(key)
+    if hit is not None and hit[0]() is images:
+        _RGBA_CACHE.move_to_end(key)
+        return hit[1]
+    src = images.detach()
+    if src.dim() == 3:
+        src = src[None]
+    if src.dtype != torch.float32:
+        src = src.float()
+    B, Cn, Hl, Wl = src.shape
+    if Cn < 3:
+        raise AssertionError("colour mode needs >= 3 image channels")
+    if src.stride(3) != 1 or src.stride(2) != Wl or src.stride(1) != Hl * Wl:
+        src = src.contiguous()
+    out = torch.empty((B, Hl, Wl, 4), dtype=torch.float32, device=src.device)
+    nat.check(nat.lib().spb_pack_rgba(src.data_ptr(), src.stride(0), B, Hl, Wl, out.data_ptr(), _stream()),
+              "spb_pack_rgba")
+    _RGBA_CACHE[key] = (weakref.ref(images), out)
+    while len(_RGBA_CACHE) > RGBA_CACHE_SIZE:
+        _RGBA_CACHE.popitem(last=False)
+    return out
+
+
+def clear_caches():
+    _GEOM_CACHE.clear()
+    _RGBA_CACHE.clear()
