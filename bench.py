@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of the dense photometric alignment hot path (BASELINE.json metric: GN-iters/sec,
+640x480, 64 primitives, two-frame alignment; HBM GB/s vs roofline for the fused kernel).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (host cores)
+
+A *step* is one Gauss-Newton/LM iteration over one batch of independent two-frame problems
+(`--pairs` per GPU, default 64 so the working set is ~0.7 GB >> 126 MB L2): one fused
+residual+Jacobian+normal-equation kernel, a fixed-order finalize and the per-problem damped solve.
+`value` = problem-iterations per second over all ranks (weak scaling: fixed pairs per GPU).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+METRIC = "GN-iters/sec (640x480, 64 primitives, two-frame alignment)"
+UNIT = "GN-iters/s"
+WORKLOAD = dict(H=480, W=640, N=64, kind="overlap")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=64, help="independent two-frame problems per GPU")
+    ap.add_argument("--mode", default="gn", choices=["gn", "grad"], help="gn = IRLS GN/LM; grad = cost+gradient")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# workload construction
+# --------------------------------------------------------------------------------------------------
+def build_batch(pairs, device, seed0=0, level=0):
+    """`pairs` distinct problems of the C2 shape at the finest pyramid level, every one with its own
+    HBM-resident geometry and images (nothing shared, so the working set scales with `pairs`)."""
+    from super_primitive_b200 import synthetic as syn
+    from super_primitive_b200.geometry import CompactGeometry, pack_rgba
+    from super_primitive_b200.solver import AlignmentBatch
+    H, W, N = WORKLOAD["H"], WORKLOAD["W"], WORKLOAD["N"]
+    src, trg, k0, pose0 = syn.two_frame_problem(H, W, N, kind=WORKLOAD["kind"], seed=seed0, noise=0.01)
+    src, trg = src.to(device), trg.to(device)
+    g = torch.Generator(device="cpu").manual_seed(seed0)
+    problems = []
+    for i in range(pairs):
+        geom = CompactGeometry(src.keypoint_regions, src.get_logdepth(), src.keypoints, src.K)
+        noise = (torch.rand(trg.image.shape, generator=g) * 0.02 - 0.01).to(device)
+        timg = (trg.image + noise).contiguous()
+        simg = (src.image + noise.flip(-1)).contiguous()
+        src_rgb = geom.source_samples(simg).clone()
+        trg_rgba = pack_rgba(timg)[0].clone()
+        dk = (torch.rand(N, generator=g) * 0.1 - 0.05)
+        pose = pose0.clone()
+        pose[:3, 3] += (torch.rand(3, generator=g) - 0.5) * 0.01
+        problems.append(dict(geom=geom, src_rgb=src_rgb, trg_rgba=trg_rgba, K_trg=trg.K, pose=pose.to(device),
+                             k=(k0 + dk).to(device)))
+    batch = AlignmentBatch(problems, with_affine=False, irls_eps=1e-3)
+    return batch, problems
+
+
+class HostStaged:
+    """End-to-end arm: every step re-uploads the step's inputs (compact geometry, cached source samples,
+    target image, pose, log-depth seeds) from pinned host memory, runs the iteration, and reads the
+    updated poses / seeds / cost back to the host."""
+
+    def __init__(self, batch, problems):
+        self.batch = batch
+        self.dev_bufs, self.host_bufs = [], []
+        seen = set()
+        for p in problems:
+            for t in (p['geom'].uv, p['geom'].logd, p['src_rgb'], p['trg_rgba']):
+                if id(t) in seen:
+                    continue
+                seen.add(id(t))
+                self.dev_bufs.append(t)
+                self.host_bufs.append(t.cpu().pin_memory())
+        self.h_pose = batch.poses.cpu().pin_memory()
+        self.h_k = batch.k.cpu().pin_memory()
+        self.o_pose = torch.empty_like(self.h_pose).pin_memory()
+        self.o_k = torch.empty_like(self.h_k).pin_memory()
+        self.o_cost = torch.empty((batch.n, 8), dtype=torch.float32).pin_memory()
+        self.h2d = sum(t.numel() * t.element_size() for t in self.host_bufs) + \
+            self.h_pose.numel() * 4 + self.h_k.numel() * 4
+        self.d2h = (self.o_pose.numel() + self.o_k.numel() + self.o_cost.numel()) * 4
+
+    def step(self):
+        b = self.batch
+        for d, h in zip(self.dev_bufs, self.host_bufs):
+            d.copy_(h, non_blocking=True)
+        b.poses.copy_(self.h_pose, non_blocking=True)
+        b.k.copy_(self.h_k, non_blocking=True)
+        b.gn_step()
+        self.o_pose.copy_(b.poses, non_blocking=True)
+        self.o_k.copy_(b.k, non_blocking=True)
+        self.o_cost.copy_(b.lm_state, non_blocking=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own PyTorch path (live import when mounted, else the pinned port)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_iter_fn():
+    """Returns (kind, callable running ONE reference iteration: photomeric_cost forward + backward +
+    Adam.step, C2 shape at the finest level)."""
+    from super_primitive_b200 import synthetic as syn
+    H, W, N = WORKLOAD["H"], WORKLOAD["W"], WORKLOAD["N"]
+    src, trg, k0, pose0 = syn.two_frame_problem(H, W, N, kind=WORKLOAD["kind"], seed=0, noise=0.01)
+    cfg = {'mode': 'colour', 'collect_stats': 0}
+    kind = "port"
+    cost = None
+    if os.path.isdir("/root/reference/core") and not os.environ.get("SPB_FORCE_PORT"):
+        try:
+            sys.dont_write_bytecode = True
+            sys.path.insert(0, "/root/reference")
+            import core.dense_optim as ref_do          # the unmodified reference
+            from image.keyframe import KeyFrame as RefKF
+            rs = RefKF(src.image, src.K, src.logdepth_perseg, src.keypoints, src.keypoint_regions)
+            rt = RefKF(trg.image, trg.K)
+            cost = lambda k, pose: ref_do.photomeric_cost(rs, rt, k, pose, cfg)   # noqa: E731
+            kind = "reference"
+        except Exception:
+            cost = None
+    if cost is None:
+        from oracle import ref_port as port
+        cost = lambda k, pose: port.cost_single(src, trg, k, pose, cfg)          # noqa: E731
+    torch.set_grad_enabled(True)
+    k = torch.nn.Parameter(k0.clone())
+    pose = torch.nn.Parameter(pose0.clone())
+    # reference learning rates, odometery/two_frame_sfm.py:117-121
+    opt = torch.optim.Adam([{'params': [k], 'lr': 1e-3}, {'params': [pose], 'lr': 1e-2}], lr=1e-3)
+
+    def one_iter():
+        loss = cost(k, pose)['residual'].mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    return kind, one_iter
+
+
+def time_cpu(steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    kind, one_iter = cpu_reference_iter_fn()
+    for _ in range(warmup):
+        one_iter()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_iter()
+    dt = time.perf_counter() - t0
+    return kind, steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    warm = max(3, args.warmup) if args.warmup else 3
+    kind, its, ms, cores = time_cpu(steps, warm)
+    sample = (f"{steps} timed iterations (after {warm} warm-up) of photomeric_cost fwd + backward + Adam.step on one "
+              f"640x480 / 64-segment pair at the finest level, float32, {cores} torch threads")
+    line = {"metric": METRIC, "value": its, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 two-frame SfM 640x480, 64 segments, finest pyramid level, 1 pair per step",
+                       "iteration": "reference PyTorch-CPU: forward + backward + Adam.step"},
+            "cpu_baseline": {"value": its, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from super_primitive_b200.shard import gather_results
+
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    batch, problems = build_batch(args.pairs, device, seed0=1000 * rank)
+    step_fn = batch.gn_step if args.mode == "gn" else batch.grad_step
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        step_fn()
+    barrier()
+    launches0 = batch.launches
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in kev:           # force creation of the native events before handing out raw handles
+        a.record()
+        b.record()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(steps):
+        step_fn(kev[i])
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    launches = batch.launches - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    pairs_total = args.pairs * world
+    value = pairs_total * steps / (total_ms * 1e-3)
+
+    # ---- end-to-end arm: host buffers in, results out, every step -------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hs = HostStaged(batch, problems)
+        e_steps = max(3, min(steps, 10))
+        for _ in range(3):
+            hs.step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e_steps):
+            hs.step()
+        b.record()
+        barrier()
+        tt = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": pairs_total * e_steps / (float(tt.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(hs.h2d), "d2h_bytes_per_step": int(hs.d2h), "steps": e_steps,
+               "what": "per step: H2D (pinned) of compact geometry + cached source samples + target image + pose + "
+                       "seeds for every pair, one GN/LM iteration, D2H of poses, seeds and LM state"}
+
+    # ---- the only collective of the path: final gather of poses / seeds / cost -------------------------
+    gather_ms = None
+    if world > 1:
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        costs = batch.lm_state[:, 1] / (3.0 * batch.pts_per_problem)
+        gather_results(batch.poses_matrix(), batch.k_padded(), costs, pairs_total)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+
+    if rank == 0:
+        alg_bytes = batch.algorithmic_bytes_per_iter(gn=(args.mode == "gn"))
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(f"{args.mode}_bytes_per_launch_{args.pairs}pairs")
+            except Exception:
+                traffic = None
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            kind, its, ms, cores = time_cpu(12, 3)
+            cpu_baseline = {"value": its, "unit": UNIT, "cores": cores, "kind": kind,
+                            "sample": "12 timed iterations (3 warm-up) of the reference iteration (photomeric_cost "
+                                      "forward + backward + Adam.step) on ONE 640x480 / 64-segment pair, finest "
+                                      f"level, float32, {cores} torch threads; {ms:.1f} ms/iter"}
+        ws = batch.points_total * 20 + sum(p['trg_rgba'].numel() * 4 for p in problems)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+                "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C2 two-frame SfM 640x480, 64 overlapping segments (P=%d points/pair), finest "
+                                       "pyramid level" % (batch.points_total // batch.n),
+                           "pairs_per_gpu": args.pairs, "iteration": "IRLS Gauss-Newton/LM" if args.mode == "gn"
+                           else "cost + first-order gradient", "parallelism": f"shard{world}",
+                           "working_set_bytes_per_gpu": int(ws), "l2": "inputs larger than L2 (126 MB), no flush"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "kernel": "k_align_global<GN>" if args.mode == "gn" else "k_align_global<GRAD>",
+                             "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": int(alg_bytes)},
+                "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        if gather_ms is not None:
+            line["final_gather_ms"] = gather_ms
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -141,16 +141,19 @@ int64_t spb_workspace_floats_points(int P);
  * (the reference uses Adam + autograd) -- oracle: oracle/closed_form.py.
  *   max_tiles : max over problems of geom.n_tiles (grid sizing)
  *   out_pair  : [n_pairs][SPB_GN_PAIR_NOUT]   out_seg : [seg_total][SPB_GN_SEG_NOUT]
- *   seg_off   : [n_pairs] offset of each problem's segments in out_seg                          */
+ *   seg_off   : [n_pairs] offset of each problem's segments in out_seg
+ *   ev_before / ev_after : optional cudaEvent_t recorded around the fused kernel alone (NULL = off) */
 int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off,
                       int n_pairs, int max_tiles, float irls_eps, int with_affine, float* work,
-                      int64_t work_stride, float* out_pair, float* out_seg, void* stream);
+                      int64_t work_stride, float* out_pair, float* out_seg, void* ev_before,
+                      void* ev_after, void* stream);
 
 /* Gradient mode over the same device-resident descriptors (batched Adam-parity iterations):
  * out_pair [n_pairs][SPB_PAIR_NOUT], out_gk [seg_total] (indexed seg_off[pair] + b). */
 int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off,
                         int n_pairs, int max_tiles, float* work, int64_t work_stride,
-                        float* out_pair, float* out_gk, void* stream);
+                        float* out_pair, float* out_gk, void* ev_before, void* ev_after,
+                        void* stream);
 
 /* CTAs per pair the batched launches use for (max_tiles, n_pairs): the workspace stride must be
  * >= ctas * nacc + max_tiles * nseg floats (nacc/nseg = 16/1 gradient, 47/10 GN). */

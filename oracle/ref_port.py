@@ -98,8 +98,9 @@ def pinhole_batch(pts, K):
     fx, fy, cx, cy = K[..., 0, 0], K[..., 1, 1], K[..., 0, 2], K[..., 1, 2]
     x, y, z = pts[..., 0], pts[..., 1], pts[..., 2]
     zi = torch.ones_like(z) * eps
-    big = torch.abs(z) > eps
-    zi[big] = 1.0 / z[big]
+    # the mask is evaluated twice (two compares + two boolean-index passes), exactly as in the
+    # reference, so that the CPU timing of this port stays representative
+    zi[torch.abs(z) > eps] = 1.0 / z[torch.abs(z) > eps]
     u = x * fx[:, None] * zi + cx[:, None]
     v = y * fy[:, None] * zi + cy[:, None]
     return torch.stack([u, v], dim=-1)

@@ -557,7 +557,7 @@ extern "C" int spb_gn_ctas(int max_tiles, int n_pairs) { return ctas_for(max_til
 
 extern "C" int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, int n_pairs,
                                  int max_tiles, float irls_eps, int with_affine, float* work, int64_t work_stride,
-                                 float* out_pair, float* out_seg, void* stream) {
+                                 float* out_pair, float* out_seg, void* ev_before, void* ev_after, void* stream) {
     if (!geoms || !pairs || !seg_off || n_pairs < 1 || max_tiles < 1 || !work || !out_pair || !out_seg)
         return SPB_EINVAL;
     if (n_pairs > 65535) return SPB_ELIMIT;
@@ -567,13 +567,16 @@ extern "C" int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, con
     const int nseg = with_affine ? Sizes<MODE_GN, 8>::NSEG : Sizes<MODE_GN, 6>::NSEG;
     if (work_stride < (int64_t)ctas * nacc + (int64_t)max_tiles * nseg) return SPB_EINVAL;
     dim3 grid(ctas, n_pairs);
+    if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
     if (with_affine) {
         k_align_global<MODE_GN, 8><<<grid, SPB_THREADS, 0, st>>>(geoms, pairs, irls_eps, work, work_stride);
         SPB_CHECK_LAUNCH();
+        if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
         k_finalize_gn<8><<<n_pairs, 128, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
     } else {
         k_align_global<MODE_GN, 6><<<grid, SPB_THREADS, 0, st>>>(geoms, pairs, irls_eps, work, work_stride);
         SPB_CHECK_LAUNCH();
+        if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
         k_finalize_gn<6><<<n_pairs, 128, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
     }
     SPB_CHECK_LAUNCH();
@@ -605,7 +608,7 @@ __global__ void k_finalize_grad_global(const SpbGeom* __restrict__ geoms, const 
 
 extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, int n_pairs,
                                    int max_tiles, float* work, int64_t work_stride, float* out_pair, float* out_gk,
-                                   void* stream) {
+                                   void* ev_before, void* ev_after, void* stream) {
     if (!geoms || !pairs || !seg_off || n_pairs < 1 || max_tiles < 1 || !work || !out_pair || !out_gk)
         return SPB_EINVAL;
     if (n_pairs > 65535) return SPB_ELIMIT;
@@ -613,8 +616,10 @@ extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, c
     const int ctas = ctas_for(max_tiles, n_pairs);
     if (work_stride < (int64_t)ctas * SPB_PAIR_NOUT + max_tiles) return SPB_EINVAL;
     dim3 grid(ctas, n_pairs);
+    if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
     k_align_global<MODE_GRAD, 6><<<grid, SPB_THREADS, 0, st>>>(geoms, pairs, 0.f, work, work_stride);
     SPB_CHECK_LAUNCH();
+    if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
     k_finalize_grad_global<<<n_pairs, 128, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_gk);
     SPB_CHECK_LAUNCH();
     return SPB_OK;

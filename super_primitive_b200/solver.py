@@ -120,11 +120,13 @@ class AlignmentBatch:
         self.launches = 0
 
     # ---- per-iteration entry points ------------------------------------------------------------
-    def gn_accumulate(self):
+    def gn_accumulate(self, ev=None):
+        """``ev`` = (torch.cuda.Event, torch.cuda.Event) recorded around the fused kernel alone."""
+        e0, e1 = (None, None) if ev is None else (ev[0].cuda_event, ev[1].cuda_event)
         nat.check(nat.lib().spb_gn_accumulate(self.d_geoms.data_ptr(), self.d_pairs.data_ptr(),
                                               self.d_seg_off.data_ptr(), self.n, self.max_tiles, self.irls_eps,
                                               1 if self.with_affine else 0, self.work.data_ptr(), self.work_stride,
-                                              self.gn_pair.data_ptr(), self.gn_seg.data_ptr(), _stream()),
+                                              self.gn_pair.data_ptr(), self.gn_seg.data_ptr(), e0, e1, _stream()),
                   "spb_gn_accumulate")
         self.launches += 2
 
@@ -137,19 +139,20 @@ class AlignmentBatch:
                                           self.saved_seg.data_ptr(), _stream()), "spb_lm_update")
         self.launches += 1
 
-    def gn_step(self):
+    def gn_step(self, ev=None):
         """One GN/LM iteration for every problem: fused residual+Jacobian+normal-equation kernel,
         finalize, damped solve + retraction."""
-        self.gn_accumulate()
+        self.gn_accumulate(ev)
         self.lm_update()
 
-    def grad_step(self):
+    def grad_step(self, ev=None):
         """Cost + first-order gradient for every problem (Adam-parity quantities): fills
         ``out_pair`` (n,16) and ``out_gk`` (seg_total,)."""
+        e0, e1 = (None, None) if ev is None else (ev[0].cuda_event, ev[1].cuda_event)
         nat.check(nat.lib().spb_grad_accumulate(self.d_geoms.data_ptr(), self.d_pairs.data_ptr(),
                                                 self.d_seg_off.data_ptr(), self.n, self.max_tiles,
                                                 self.work.data_ptr(), self.work_stride, self.out_pair.data_ptr(),
-                                                self.out_gk.data_ptr(), _stream()), "spb_grad_accumulate")
+                                                self.out_gk.data_ptr(), e0, e1, _stream()), "spb_grad_accumulate")
         self.launches += 2
 
     def run_gn(self, iters):

@@ -160,9 +160,12 @@ CONFIGS = {
 
 def two_frame_problem(H, W, N, kind="strips", seed=0, noise=0.0, shift=(2.0, 1.0)):
     """Source keyframe with geometry + a supporting target frame whose image is the same
-    scene displaced by ``shift`` pixels; initial log-depth seeds log 2; initial pose 2 cm in x."""
+    scene displaced by ``shift`` pixels; initial log-depth seeds log 2; initial pose ~2 cm translation + a few mrad rotation."""
     src = make_keyframe(H, W, N, kind=kind, seed=seed, noise=noise)
     trg = make_keyframe(H, W, N, shift=shift, noise=noise, seed=seed + 1, supporting=True)
     k0 = torch.full((N,), math.log(2.0), dtype=torch.float32)
-    pose0 = small_pose(0.02, 0.0, 0.0)
+    # generic position on purpose: with an axis-aligned integer-pixel displacement every warped point
+    # lands exactly on a texel row/column, where the slope of bilinear interpolation is discontinuous
+    # and float32 rounding (in the reference too) decides which side is taken
+    pose0 = small_pose(0.02, 0.004, -0.003, 0.003, -0.002, 0.0015)
     return src, trg, k0, pose0

@@ -9,6 +9,10 @@ from tests.common import Golden, assert_close, to_np
 
 pytestmark = pytest.mark.gpu
 
+# IRLS weights 1/max(|r|, eps) amplify float32 rounding of small residuals (d w / w = d r / r), so the
+# float32 blocks are compared with the float64 oracle at 1e-3 (scale-relative), the cost at 2e-5.
+GN_TOL = 1e-3
+
 
 def _tri8(A8):
     out = np.zeros((8, 8))
@@ -47,13 +51,13 @@ def test_normal_equations_match_closed_form(case, with_affine):
             gs = to_np(batch.gn_seg[j * g.N:(j + 1) * g.N]).astype(np.float64)
             A = _tri8(gp[:36])
             np_ = 8 if with_affine else 6
-            assert_close(A[:np_, :np_], r["A"], 2e-4, f"A (pair {j}, level {lvl})")
-            assert_close(gp[36:36 + np_], r["g_p"], 2e-4, "g_p")
-            assert_close(gs[:, :np_].T, r["B"], 2e-4, "B")
-            assert_close(gs[:, 8], r["D"], 2e-4, "D")
-            assert_close(gs[:, 9], r["g_d"], 2e-4, "g_d")
+            assert_close(A[:np_, :np_], r["A"], GN_TOL, f"A (pair {j}, level {lvl})")
+            assert_close(gp[36:36 + np_], r["g_p"], GN_TOL, "g_p")
+            assert_close(gs[:, :np_].T, r["B"], GN_TOL, "B")
+            assert_close(gs[:, 8], r["D"], GN_TOL, "D")
+            assert_close(gs[:, 9], r["g_d"], GN_TOL, "g_d")
             assert_close(gp[44] / (3 * r["P"]), r["cost"], 2e-5, "cost")
-            assert_close(gp[45], r["wcost"], 2e-4, "weighted cost")
+            assert_close(gp[45], r["wcost"], GN_TOL, "weighted cost")
             if not with_affine:
                 assert np.all(A[6:, :] == 0) and np.all(gs[:, 6:8] == 0)
 
