@@ -63,7 +63,7 @@ __device__ __forceinline__ void eval_point(const float* __restrict__ c, const fl
     const float Yy = RXy + c[C_T + 1];
     const float Yz = RXz + c[C_T + 2];
     const bool live = fabsf(Yz) > 1e-6f;                       // guarded reciprocal, core/ops.py:22,33-34
-    const float zi = live ? (1.0f / Yz) : 1e-6f;
+    const float zi = live ? __fdividef(1.0f, Yz) : 1e-6f;     // MUFU.RCP, <= 1 ulp
     const float up = fmaf(Yx * c[C_FXT], zi, c[C_CXT]);
     const float vp = fmaf(Yy * c[C_FYT], zi, c[C_CYT]);
     const float xn = fmaf(up, c[C_TIW], -1.0f);
@@ -112,7 +112,7 @@ __device__ __forceinline__ void eval_point(const float* __restrict__ c, const fl
     const float fxf = floorf(ix), fyf = floorf(iy);
     const int x0 = (int)fxf, y0 = (int)fyf;
     const float fx = ix - fxf, fy = iy - fyf;
-    const float4* p0 = trg + (size_t)y0 * Wl + x0;
+    const float4* p0 = trg + (y0 * Wl + x0);                   // 32-bit texel index (image < 2^31 texels)
     const float4 nw = __ldg(p0), ne = __ldg(p0 + 1);
     const float4 sw = __ldg(p0 + Wl), se = __ldg(p0 + Wl + 1);
 
@@ -311,27 +311,227 @@ __device__ __forceinline__ void align_body(const SpbGeom& g, const SpbPair& pr, 
     block_reduce_store<NACC>(acc, s_red, part_pair + (size_t)blockIdx.x * NACC);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multi-value warp reduction: N per-lane values -> N warp sums with ~N+2 shuffles instead of 5N.
+// The first 8 values are folded with a butterfly that halves the value set at every exchange
+// (4+2+1 shuffles), then two more exchanges finish the sum; lane 4*i holds the total of value i.
+// Fixed exchange order => deterministic.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restrict__ dst, int lane) {
+    if constexpr (N >= 8) {
+        float a[4], b[2], c1;
+        const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = up16 ? v[i] : v[i + 4];
+            const float keep = up16 ? v[i + 4] : v[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = up8 ? a[i] : a[i + 2];
+            const float keep = up8 ? a[i + 2] : a[i];
+            b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const float send = up4 ? b[0] : b[1];
+            const float keep = up4 ? b[1] : b[0];
+            c1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, 1);
+        if ((lane & 3) == 0) dst[lane >> 2] = c1;
+#pragma unroll
+        for (int i = 8; i < N; ++i) {
+            const float t = warp_sum(v[i]);
+            if (lane == 0) dst[i] = t;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const float t = warp_sum(v[i]);
+            if (lane == 0) dst[i] = t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bulk-async (TMA 1-D) staging of the streaming point arrays through a shared-memory ring.
+// A CTA owns chunks of SPB_WARPS consecutive tiles (<= 1024 points + inter-segment padding, one
+// contiguous range of the padded point arrays); one thread issues 5 cp.async.bulk copies per
+// chunk (uv, logd, r, g, b) that complete on an mbarrier, STAGES-1 chunks ahead of the consumers.
+// The streaming operands therefore never occupy registers and never stall a warp; only the four
+// bilinear taps of the target image are register loads.
+// ------------------------------------------------------------------------------------------------
+#define SPB_CAP (SPB_WARPS * SPB_TILE + 32)          // points per stage (tiles + <=3-point gaps, rounded)
+#define SPB_STAGES 3
+#define SPB_STAGE_WORDS (5 * SPB_CAP)
+#define SPB_DYN_SMEM (SPB_STAGES * SPB_STAGE_WORDS * 4 + 64)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+
+template <int MODE, int NP>
+__device__ __forceinline__ void align_body_staged(const SpbGeom& g, const SpbPair& pr, float irls_eps,
+                                                  float* __restrict__ part_pair, float* __restrict__ part_seg) {
+    constexpr int NACC = Sizes<MODE, NP>::NACC;
+    constexpr int NSEG = Sizes<MODE, NP>::NSEG;
+    extern __shared__ __align__(128) uint32_t s_dyn[];
+    __shared__ float s_ctx[C_N];
+    __shared__ float s_red[SPB_WARPS * NACC];
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_dyn + SPB_STAGES * SPB_STAGE_WORDS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int4* tiles = reinterpret_cast<const int4*>(g.tiles);
+    const int nchunks = (g.n_tiles + SPB_WARPS - 1) / SPB_WARPS;
+    const int G = gridDim.x;
+
+    if (threadIdx.x < 32) fill_ctx(s_ctx, pr, g.K, g.H, g.W);
+    if (threadIdx.x == 32) {
+#pragma unroll
+        for (int s = 0; s < SPB_STAGES; ++s) mbar_init(smem_u32(s_bar + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const float* c = s_ctx;
+
+    // producer: chunk `ch` -> ring slot `slot`
+    auto issue = [&](int ch, int slot) {
+        const int t0 = ch * SPB_WARPS;
+        const int t1 = min(t0 + SPB_WARPS, g.n_tiles);
+        const int4 a = __ldg(tiles + t0), b = __ldg(tiles + t1 - 1);
+        const int p0 = a.y;
+        const int npts = (b.y + b.z - p0 + 3) & ~3;
+        const uint32_t bytes = (uint32_t)npts * 4u;
+        const uint32_t bar = smem_u32(s_bar + slot);
+        const uint32_t dst = smem_u32(s_dyn + slot * SPB_STAGE_WORDS);
+        mbar_expect_tx(bar, 5u * bytes);
+        bulk_g2s(dst, g.uv + p0, bytes, bar);
+        bulk_g2s(dst + SPB_CAP * 4, g.logd + p0, bytes, bar);
+        bulk_g2s(dst + 2 * SPB_CAP * 4, pr.src_rgb + p0, bytes, bar);
+        bulk_g2s(dst + 3 * SPB_CAP * 4, pr.src_rgb + (size_t)g.n_pad + p0, bytes, bar);
+        bulk_g2s(dst + 4 * SPB_CAP * 4, pr.src_rgb + 2 * (size_t)g.n_pad + p0, bytes, bar);
+    };
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < SPB_STAGES - 1; ++s) {
+            const int ch = blockIdx.x + s * G;
+            if (ch < nchunks) issue(ch, s);
+        }
+    }
+
+    const float4* trg = reinterpret_cast<const float4*>(pr.trg_rgba);
+    const int Wl = pr.Wl, Hl = pr.Hl;
+    PointOut po{nullptr, 0, g.n_pts};
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+
+    int it = 0;
+    for (int ch = blockIdx.x; ch < nchunks; ch += G, ++it) {
+        const int slot = it % SPB_STAGES;
+        __syncthreads();                                   // every warp is done with the slot refilled below
+        if (threadIdx.x == 0) {
+            const int nx = ch + (SPB_STAGES - 1) * G;
+            if (nx < nchunks) issue(nx, (it + SPB_STAGES - 1) % SPB_STAGES);
+        }
+        mbar_wait(smem_u32(s_bar + slot), (uint32_t)((it / SPB_STAGES) & 1));
+        const int t = ch * SPB_WARPS + warp;
+        if (t < g.n_tiles) {
+            const int p0 = __ldg(&tiles[ch * SPB_WARPS].y);
+            const int4 td = __ldg(tiles + t);
+            const int cnt = td.z;
+            const uint32_t* st_uv = s_dyn + slot * SPB_STAGE_WORDS + (td.y - p0);
+            const float* st_l = reinterpret_cast<const float*>(st_uv) + SPB_CAP;
+            const float shift = __ldg(pr.k + td.x) - __ldg(g.seg_lkp + td.x);
+            float seg[NSEG];
+#pragma unroll
+            for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < SPB_PPT; ++j) {
+                const int i = j * 32 + lane;
+                if (i < cnt) {
+                    const uint32_t w = st_uv[i];
+                    const float u = (float)(w & 0xffffu);
+                    const float v = (float)((w >> 16) & 0x7fffu);
+                    const float z = __expf(st_l[i] + shift);
+                    const float Xx = (u - c[C_CX]) * z * c[C_IFX];
+                    const float Xy = (v - c[C_CY]) * z * c[C_IFY];
+                    const bool sok = (w >> 31) && (z > 1e-7f);
+                    eval_point<MODE, NP, false, NACC, NSEG>(c, trg, Wl, Hl, Xx, Xy, z, sok, st_l[SPB_CAP + i],
+                                                            st_l[2 * SPB_CAP + i], st_l[3 * SPB_CAP + i], irls_eps,
+                                                            acc, seg, po, 0);
+                }
+            }
+            tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
+        }
+    }
+    __syncthreads();
+    block_reduce_store<NACC>(acc, s_red, part_pair + (size_t)blockIdx.x * NACC);
+}
+
 struct PairPack {
     SpbPair p[16];
 };
 
+// occupancy target: 3 CTAs/SM (<= 80 registers) for the gradient kernel, 2 for the GN kernel whose
+// 38 accumulators do not fit 80 registers without spilling
+template <int MODE>
+struct Occ { static constexpr int CTAS = (MODE == MODE_GRAD) ? 3 : 2; };
+
 // B pairs over one geometry, descriptors by value (Python per-call path: no descriptor upload)
-template <int MODE, int NP, bool STATS>
-__global__ void __launch_bounds__(SPB_THREADS, 2)
+template <int MODE, int NP>
+__global__ void __launch_bounds__(SPB_THREADS, Occ<MODE>::CTAS)
 k_align_inline(const __grid_constant__ SpbGeom g, const __grid_constant__ PairPack pack, float irls_eps,
-               float* __restrict__ work, SpbStats stats) {
+               float* __restrict__ work) {
     constexpr int NACC = Sizes<MODE, NP>::NACC;
     constexpr int NSEG = Sizes<MODE, NP>::NSEG;
     const int pair = blockIdx.y;
     const size_t stride = (size_t)gridDim.x * NACC + (size_t)g.n_tiles * NSEG;
     float* base = work + pair * stride;
-    align_body<MODE, NP, STATS>(g, pack.p[pair], pair, irls_eps, base, base + (size_t)gridDim.x * NACC,
-                                STATS ? &stats : nullptr);
+    align_body_staged<MODE, NP>(g, pack.p[pair], irls_eps, base, base + (size_t)gridDim.x * NACC);
+}
+
+// same, slow path that also materialises the per-point statistics (register-prefetch body)
+__global__ void __launch_bounds__(SPB_THREADS, 2)
+k_align_stats(const __grid_constant__ SpbGeom g, const __grid_constant__ PairPack pack, float* __restrict__ work,
+              SpbStats stats) {
+    constexpr int NACC = Sizes<MODE_GRAD, 6>::NACC;
+    constexpr int NSEG = Sizes<MODE_GRAD, 6>::NSEG;
+    const int pair = blockIdx.y;
+    const size_t stride = (size_t)gridDim.x * NACC + (size_t)g.n_tiles * NSEG;
+    float* base = work + pair * stride;
+    align_body<MODE_GRAD, 6, true>(g, pack.p[pair], pair, 0.f, base, base + (size_t)gridDim.x * NACC, &stats);
 }
 
 // n_pairs independent problems, descriptors in device memory (batched solver / benchmark path)
 template <int MODE, int NP>
-__global__ void __launch_bounds__(SPB_THREADS, 2)
+__global__ void __launch_bounds__(SPB_THREADS, Occ<MODE>::CTAS)
 k_align_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs, float irls_eps,
                float* __restrict__ work, int64_t work_stride) {
     constexpr int NACC = Sizes<MODE, NP>::NACC;
@@ -344,7 +544,7 @@ k_align_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pa
     }
     __syncthreads();
     float* base = work + pair * work_stride;
-    align_body<MODE, NP, false>(s_g, s_pr, pair, irls_eps, base, base + (size_t)gridDim.x * NACC, nullptr);
+    align_body_staged<MODE, NP>(s_g, s_pr, irls_eps, base, base + (size_t)gridDim.x * NACC);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -362,11 +562,13 @@ __global__ void k_finalize_grad(const __grid_constant__ SpbGeom g, int ctas, con
         for (int cta = 0; cta < ctas; ++cta) v += pp[(size_t)cta * SPB_PAIR_NOUT + threadIdx.x];
         out_pair[pair * SPB_PAIR_NOUT + threadIdx.x] = (threadIdx.x == 15) ? v : v * norm;
     }
-    for (int b = threadIdx.x; b < g.n_seg; b += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int b = warp; b < g.n_seg; b += nwarps) {
         float v = 0.f;
         const int t1 = g.seg_tile[b + 1];
-        for (int t = g.seg_tile[b]; t < t1; ++t) v += ps[t];
-        out_gk[(size_t)pair * g.n_seg + b] = v * norm;
+        for (int t = g.seg_tile[b] + lane; t < t1; t += 32) v += ps[t];
+        v = warp_sum(v);
+        if (lane == 0) out_gk[(size_t)pair * g.n_seg + b] = v * norm;
     }
 }
 
@@ -421,23 +623,28 @@ __global__ void k_finalize_gn(const SpbGeom* __restrict__ geoms, const SpbPair* 
     }
     if (NP == 8 && threadIdx.x == SPB_GN_PAIR_NOUT - 1) op[threadIdx.x] = 0.f;
     const int so = seg_off[pair];
-    for (int b = threadIdx.x; b < g.n_seg; b += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int b = warp; b < g.n_seg; b += nwarps) {          // one warp per segment, lanes stride its tiles
         float v[NSEG];
 #pragma unroll
         for (int i = 0; i < NSEG; ++i) v[i] = 0.f;
         const int t1 = g.seg_tile[b + 1];
-        for (int t = g.seg_tile[b]; t < t1; ++t) {
+        for (int t = g.seg_tile[b] + lane; t < t1; t += 32) {
 #pragma unroll
             for (int i = 0; i < NSEG; ++i) v[i] += ps[(size_t)t * NSEG + i];
         }
-        float* os = out_seg + (size_t)(so + b) * SPB_GN_SEG_NOUT;
-        if (NP == 8) {
 #pragma unroll
-            for (int i = 0; i < 10; ++i) os[i] = v[i];
-        } else {
+        for (int i = 0; i < NSEG; ++i) v[i] = warp_sum(v[i]);
+        if (lane == 0) {
+            float* os = out_seg + (size_t)(so + b) * SPB_GN_SEG_NOUT;
+            if (NP == 8) {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) os[i] = v[i];
-            os[6] = 0.f; os[7] = 0.f; os[8] = v[6]; os[9] = v[7];
+                for (int i = 0; i < 10; ++i) os[i] = v[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) os[i] = v[i];
+                os[6] = 0.f; os[7] = 0.f; os[8] = v[6]; os[9] = v[7];
+            }
         }
     }
 }
@@ -489,12 +696,18 @@ __global__ void k_finalize_points(int ctas, int P, const float* __restrict__ wor
 // host-side launch helpers (C ABI)
 // ------------------------------------------------------------------------------------------------
 static inline int ctas_for(int n_tiles, int n_pairs) {
-    int want = (n_tiles + SPB_WARPS - 1) / SPB_WARPS;               // one tile per warp
-    int cap = (148 * 8) / (n_pairs > 0 ? n_pairs : 1);              // ~4 waves of 2 CTAs/SM in total
-    if (cap < 1) cap = 1;
-    if (want > cap) want = cap;
+    // a CTA streams chunks of SPB_WARPS tiles; aim at ~4 waves of 3 CTAs/SM over all pairs so the
+    // tail wave is small, but never more CTAs than chunks
+    const int nchunks = (n_tiles + SPB_WARPS - 1) / SPB_WARPS;
+    int want = (148 * 3 * 4 + n_pairs - 1) / (n_pairs > 0 ? n_pairs : 1);
+    if (want > nchunks) want = nchunks;
     if (want < 1) want = 1;
     return want;
+}
+
+template <typename K>
+static inline cudaError_t allow_dyn_smem(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_DYN_SMEM);
 }
 
 static inline int ctas_for_points(int P) {
@@ -529,13 +742,14 @@ extern "C" int spb_cost_grad(const SpbGeom* geom, const SpbPair* pairs, int B, f
     const int ctas = ctas_for(geom->n_tiles, B);
     dim3 grid(ctas, B);
     if (stats) {
-        k_align_inline<MODE_GRAD, 6, true><<<grid, SPB_THREADS, 0, st>>>(*geom, pack, 0.f, work, *stats);
+        k_align_stats<<<grid, SPB_THREADS, 0, st>>>(*geom, pack, work, *stats);
     } else {
-        SpbStats none = {};
-        k_align_inline<MODE_GRAD, 6, false><<<grid, SPB_THREADS, 0, st>>>(*geom, pack, 0.f, work, none);
+        cudaError_t e = allow_dyn_smem(k_align_inline<MODE_GRAD, 6>);
+        if (e != cudaSuccess) return (int)e;
+        k_align_inline<MODE_GRAD, 6><<<grid, SPB_THREADS, SPB_DYN_SMEM, st>>>(*geom, pack, 0.f, work);
     }
     SPB_CHECK_LAUNCH();
-    k_finalize_grad<<<B, 128, 0, st>>>(*geom, ctas, work, out_pair, out_gk);
+    k_finalize_grad<<<B, 256, 0, st>>>(*geom, ctas, work, out_pair, out_gk);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
@@ -569,15 +783,19 @@ extern "C" int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, con
     dim3 grid(ctas, n_pairs);
     if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
     if (with_affine) {
-        k_align_global<MODE_GN, 8><<<grid, SPB_THREADS, 0, st>>>(geoms, pairs, irls_eps, work, work_stride);
+        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GN, 8>);
+        if (e != cudaSuccess) return (int)e;
+        k_align_global<MODE_GN, 8><<<grid, SPB_THREADS, SPB_DYN_SMEM, st>>>(geoms, pairs, irls_eps, work, work_stride);
         SPB_CHECK_LAUNCH();
         if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
-        k_finalize_gn<8><<<n_pairs, 128, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
+        k_finalize_gn<8><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
     } else {
-        k_align_global<MODE_GN, 6><<<grid, SPB_THREADS, 0, st>>>(geoms, pairs, irls_eps, work, work_stride);
+        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GN, 6>);
+        if (e != cudaSuccess) return (int)e;
+        k_align_global<MODE_GN, 6><<<grid, SPB_THREADS, SPB_DYN_SMEM, st>>>(geoms, pairs, irls_eps, work, work_stride);
         SPB_CHECK_LAUNCH();
         if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
-        k_finalize_gn<6><<<n_pairs, 128, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
+        k_finalize_gn<6><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
     }
     SPB_CHECK_LAUNCH();
     return SPB_OK;
@@ -598,11 +816,13 @@ __global__ void k_finalize_grad_global(const SpbGeom* __restrict__ geoms, const 
         out_pair[pair * SPB_PAIR_NOUT + threadIdx.x] = (threadIdx.x == 15) ? v : v * norm;
     }
     const int so = seg_off[pair];
-    for (int b = threadIdx.x; b < g.n_seg; b += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int b = warp; b < g.n_seg; b += nwarps) {
         float v = 0.f;
         const int t1 = g.seg_tile[b + 1];
-        for (int t = g.seg_tile[b]; t < t1; ++t) v += ps[t];
-        out_gk[so + b] = v * norm;
+        for (int t = g.seg_tile[b] + lane; t < t1; t += 32) v += ps[t];
+        v = warp_sum(v);
+        if (lane == 0) out_gk[so + b] = v * norm;
     }
 }
 
@@ -617,10 +837,12 @@ extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, c
     if (work_stride < (int64_t)ctas * SPB_PAIR_NOUT + max_tiles) return SPB_EINVAL;
     dim3 grid(ctas, n_pairs);
     if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
-    k_align_global<MODE_GRAD, 6><<<grid, SPB_THREADS, 0, st>>>(geoms, pairs, 0.f, work, work_stride);
+    cudaError_t e = allow_dyn_smem(k_align_global<MODE_GRAD, 6>);
+    if (e != cudaSuccess) return (int)e;
+    k_align_global<MODE_GRAD, 6><<<grid, SPB_THREADS, SPB_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
     SPB_CHECK_LAUNCH();
     if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
-    k_finalize_grad_global<<<n_pairs, 128, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_gk);
+    k_finalize_grad_global<<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_gk);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

@@ -144,9 +144,11 @@ class _PairCost(torch.autograd.Function):
         out_pair, out_gk = _launch_pairs(geom, src_rgb, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau)
         if check:
             # the reference asserts finiteness at five sites per call (core/dense_optim.py:44,78,311,
-            # 321,340-343); one flag read covers inputs and outputs here
-            if not bool(torch.isfinite(out_pair).all()):
-                raise AssertionError("non-finite photometric cost or gradient (inputs not finite?)")
+            # 321,340-343); one flag read (one sync) covers inputs and outputs here.  A NaN seed would
+            # otherwise just invalidate its points, so the inputs are tested explicitly.
+            ok = torch.isfinite(out_pair).all() & torch.isfinite(k_c).all() & torch.isfinite(poses_c).all()
+            if not bool(ok):
+                raise AssertionError("non-finite photometric cost, gradient or input (log-depth / pose)")
         ctx.save_for_backward(out_pair, out_gk)
         ctx.shapes = (None if aff_src is None else aff_src.shape, None if aff_trg is None else aff_trg.shape,
                       poses.shape)
@@ -366,14 +368,14 @@ class _PointsCost(torch.autograd.Function):
         P = src_pts.shape[0]
         dev = pose_c.device
         pr = nat.SpbPair(trg_rgba.data_ptr(), None, trg_K.data_ptr(), pose_c.data_ptr(), None, nat.ptr(a_s),
-                         nat.ptr(a_t), 0, trg_rgba.shape[1], trg_rgba.shape[2], 1e-7)
+                         nat.ptr(a_t), 0, trg_rgba.shape[0], trg_rgba.shape[1], 1e-7)
         work = torch.empty(lib.spb_workspace_floats_points(P), dtype=torch.float32, device=dev)
         out_pair = torch.empty(nat.PAIR_NOUT, dtype=torch.float32, device=dev)
         nat.check(lib.spb_cost_grad_points(src_pts.data_ptr(), src_px.data_ptr(), src_ok.data_ptr(), P,
                                            int(dims[0]), int(dims[1]), C.byref(pr), work.data_ptr(),
                                            out_pair.data_ptr(), _stream()), "spb_cost_grad_points")
-        if check and not bool(torch.isfinite(out_pair).all()):
-            raise AssertionError("non-finite photometric cost or gradient")
+        if check and not bool(torch.isfinite(out_pair).all() & torch.isfinite(pose_c).all()):
+            raise AssertionError("non-finite photometric cost, gradient or pose")
         ctx.save_for_backward(out_pair)
         ctx.shapes = (None if aff_src is None else aff_src.shape, None if aff_trg is None else aff_trg.shape)
         return out_pair[0:1].clone()

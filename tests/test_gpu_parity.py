@@ -194,7 +194,7 @@ def test_adam_trajectory():
         opt.zero_grad()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
         if i in (0, 9, 19, steps - 1):
             assert_close(to_np(k), z["traj_k"][i], TOL, f"k after step {i}")
             assert np.abs(to_np(xi) - z["traj_xi"][i]).max() <= TOL * max(np.abs(z["traj_xi"][i]).max(), 1.0), \
@@ -213,16 +213,30 @@ def test_fresh_inputs_against_cpu_oracle(kind, H, W, N):
     spyr, tpyr = syn.keyframe_pyramid(src0, 0, 3), syn.keyframe_pyramid(trg0, 0, 3)
     k0 = torch.full((N,), float(np.log(2.0))) + 0.1 * torch.randn(N, generator=torch.Generator().manual_seed(1))
     pose0 = syn.small_pose(0.02, 0.01, -0.01, 0.02, -0.01, 0.015)
+    def f64(kf):
+        from super_primitive_b200.keyframe import KeyFrame
+        c = lambda t: None if t is None else (t.double() if t.is_floating_point() else t)   # noqa: E731
+        return KeyFrame(c(kf.image), c(kf.K), c(kf.logdepth_perseg), c(kf.keypoints), kf.keypoint_regions, c(kf.K_img))
+
     for s, t_ in zip(spyr, tpyr):
+        # float32 port == what the reference computes; float64 port == what it is approximating.  The
+        # float32 reference itself is only accurate to ~1e-4..1e-3 on cancelling gradient sums, so the GPU is
+        # held to 1e-4 against the float64 run and the float32 run is checked to sit in the same band.
         k, pose = _leaf(k0), _leaf(pose0)
         ref = port.cost_single(s, t_, k, pose, CFG0)
         ref['residual'].mean().backward()
+        k64, pose64 = _leaf(k0.double()), _leaf(pose0.double())
+        ref64 = port.cost_single(f64(s), f64(t_), k64, pose64, CFG0)
+        ref64['residual'].mean().backward()
         kg, pg = _leaf(k0.cuda()), _leaf(pose0.cuda())
         out = do.photomeric_cost(s.to("cuda"), t_.to("cuda"), kg, pg, CFG0)
         out['residual'].mean().backward()
-        assert_close(to_np(out['residual']), to_np(ref['residual']), 2e-5, "residual")
-        assert_close(to_np(kg.grad), to_np(k.grad), TOL, "g_k")
-        assert_close(to_np(pg.grad), to_np(pose.grad), TOL, "g_pose")
+        assert_close(to_np(out['residual']), to_np(ref64['residual']), 2e-5, "residual vs float64")
+        assert_close(to_np(out['residual']), to_np(ref['residual']), 2e-5, "residual vs float32")
+        assert_close(to_np(kg.grad), to_np(k64.grad), TOL, "g_k vs float64")
+        assert_close(to_np(pg.grad), to_np(pose64.grad), TOL, "g_pose vs float64")
+        assert_close(to_np(kg.grad), to_np(k.grad), 1e-3, "g_k vs float32")
+        assert_close(to_np(pg.grad), to_np(pose.grad), 1e-3, "g_pose vs float32")
 
 
 def test_non_finite_inputs_raise_assertion():
