@@ -151,7 +151,7 @@ int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t*
 /* Gradient mode over the same device-resident descriptors (batched Adam-parity iterations):
  * out_pair [n_pairs][SPB_PAIR_NOUT], out_gk [seg_total] (indexed seg_off[pair] + b). */
 int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off,
-                        int n_pairs, int max_tiles, float* work, int64_t work_stride,
+                        int n_pairs, int max_tiles, int with_affine, float* work, int64_t work_stride,
                         float* out_pair, float* out_gk, void* ev_before, void* ev_after,
                         void* stream);
 
@@ -189,6 +189,13 @@ int spb_depth_splat(const SpbGeom* geom, const float* k, const float* pose /* NU
 /* lifted points of a keyframe: src_pts [n][3] (core/dense_optim.py:176-200) */
 int spb_lift_points(const SpbGeom* geom, const float* k, float* src_pts, int64_t* seg_ids,
                     uint8_t* src_ok, void* stream);
+
+/* Per-segment re-initialisation of the log-depth seeds from a depth map (odometery/depth_init.py:10-67):
+ * mode 0 = mean, 1 = lower median of log(est) - L over the segment's valid pixels (est >= 1e-6), plus the
+ * log-depth at the keypoint; invisible segments receive the lower median of the visible ones.
+ * est_depth [H][W]; seg_val [N] scratch; visible [N] out; out_k [N] out; n_visible [1] out (may be NULL). */
+int spb_segment_reinit(const SpbGeom* geom, const float* est_depth, int mode, float* seg_val,
+                       uint8_t* visible, float* out_k, int32_t* n_visible, void* stream);
 
 /* version / build info */
 int spb_version(void);

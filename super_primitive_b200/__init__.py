@@ -27,3 +27,13 @@ def install_as_core(force=True):
         sys.modules[f"core.{name}"] = mod
         setattr(pkg, name, mod)
     return pkg
+
+
+def install_depth_init():
+    """Also route ``odometery.depth_init`` (segment_based_depth_reinit) to the CUDA path.  Call before
+    ``odometery.odometery`` / ``depth_completion`` are imported; the rest of the reference's ``odometery``
+    package stays the reference's."""
+    import importlib
+    mod = importlib.import_module(f"{__name__}.depth_init")
+    sys.modules["odometery.depth_init"] = mod
+    return mod

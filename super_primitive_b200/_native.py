@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libspb200.so")
+LIB_PATH = os.environ.get("SPB200_LIB") or os.path.join(_HERE, "csrc", "libspb200.so")   # env: tuning variants only
 
 TILE = 128
 PAD = 4
@@ -60,12 +60,13 @@ _PROTOS = {
     "spb_workspace_floats_points": (_i64, [_i]),
     "spb_gn_ctas": (_i, [_i, _i]),
     "spb_gn_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "spb_grad_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "spb_grad_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "spb_lm_saved_floats": (_i, [_i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
     "spb_lm_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spb_dense_depths": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "spb_depth_splat": (_i, [C.POINTER(SpbGeom), _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "spb_lift_points": (_i, [C.POINTER(SpbGeom), _vp, _vp, _vp, _vp, _vp]),
+    "spb_segment_reinit": (_i, [C.POINTER(SpbGeom), _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "spb_version": (_i, []),
 }
 

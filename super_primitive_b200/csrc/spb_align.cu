@@ -357,139 +357,109 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Bulk-async (TMA 1-D) staging of the streaming point arrays through a shared-memory ring.
-// A CTA owns chunks of SPB_WARPS consecutive tiles (<= 1024 points + inter-segment padding, one
-// contiguous range of the padded point arrays); one thread issues 5 cp.async.bulk copies per
-// chunk (uv, logd, r, g, b) that complete on an mbarrier, STAGES-1 chunks ahead of the consumers.
-// The streaming operands therefore never occupy registers and never stall a warp; only the four
-// bilinear taps of the target image are register loads.
-// ------------------------------------------------------------------------------------------------
-#define SPB_CAP (SPB_WARPS * SPB_TILE + 32)          // points per stage (tiles + <=3-point gaps, rounded)
-#define SPB_STAGES 3
-#define SPB_STAGE_WORDS (5 * SPB_CAP)
-#define SPB_DYN_SMEM (SPB_STAGES * SPB_STAGE_WORDS * 4 + 64)
+#include "spb_fast.cuh"
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
-}
-
-template <int MODE, int NP>
-__device__ __forceinline__ void align_body_staged(const SpbGeom& g, const SpbPair& pr, float irls_eps,
-                                                  float* __restrict__ part_pair, float* __restrict__ part_seg) {
+// ------------------------------------------------------------------------------------------------
+// Hot-path body: per-warp bulk-async pipelines (see spb_fast.cuh).  grid = (ctas_per_pair, pairs)
+//   part_pair : [cta][NACC]      part_seg : [tile][NSEG]
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int NP, bool AFF>
+__device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair& pr, float irls_eps,
+                                                float* __restrict__ part_pair, float* __restrict__ part_seg) {
     constexpr int NACC = Sizes<MODE, NP>::NACC;
     constexpr int NSEG = Sizes<MODE, NP>::NSEG;
     extern __shared__ __align__(128) uint32_t s_dyn[];
-    __shared__ float s_ctx[C_N];
+    __shared__ __align__(16) float s_ctx[F_N];
+    __shared__ float s_shift[SPB_NSHIFT];
     __shared__ float s_red[SPB_WARPS * NACC];
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_dyn + SPB_STAGES * SPB_STAGE_WORDS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* ring = s_dyn + warp * (SPB_WSTAGES * SPB_SLOT_WORDS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + SPB_WARPS * SPB_WSTAGES * SPB_SLOT_WORDS) + warp * SPB_WSTAGES;
     const int4* tiles = reinterpret_cast<const int4*>(g.tiles);
-    const int nchunks = (g.n_tiles + SPB_WARPS - 1) / SPB_WARPS;
-    const int G = gridDim.x;
 
-    if (threadIdx.x < 32) fill_ctx(s_ctx, pr, g.K, g.H, g.W);
-    if (threadIdx.x == 32) {
+    if (threadIdx.x < 32) fill_fast_ctx(s_ctx, pr, g.K, g.H, g.W);
+    if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < SPB_STAGES; ++s) mbar_init(smem_u32(s_bar + s), 1);
+        for (int s = 0; s < SPB_WSTAGES; ++s) mbar_init(smem_u32(bars + s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    const int nshift = min(g.n_seg, SPB_NSHIFT);
+    for (int b = threadIdx.x; b < nshift; b += blockDim.x) s_shift[b] = __ldg(pr.k + b) - __ldg(g.seg_lkp + b);
     __syncthreads();
     const float* c = s_ctx;
 
-    // producer: chunk `ch` -> ring slot `slot`
-    auto issue = [&](int ch, int slot) {
-        const int t0 = ch * SPB_WARPS;
-        const int t1 = min(t0 + SPB_WARPS, g.n_tiles);
-        const int4 a = __ldg(tiles + t0), b = __ldg(tiles + t1 - 1);
-        const int p0 = a.y;
-        const int npts = (b.y + b.z - p0 + 3) & ~3;
-        const uint32_t bytes = (uint32_t)npts * 4u;
-        const uint32_t bar = smem_u32(s_bar + slot);
-        const uint32_t dst = smem_u32(s_dyn + slot * SPB_STAGE_WORDS);
+    const int WS = gridDim.x * SPB_WARPS;                  // tile stride of this warp
+    const int t_first = blockIdx.x * SPB_WARPS + warp;
+    const size_t plane = (size_t)g.n_pad;
+
+    auto issue = [&](const int4 td, int slot) {            // lane 0: descriptor + 5 bulk copies -> ring slot
+        uint32_t* sl = ring + slot * SPB_SLOT_WORDS;
+        sl[0] = (uint32_t)td.x; sl[1] = (uint32_t)td.z; sl[2] = (uint32_t)td.w;
+        const uint32_t bytes = (uint32_t)((td.z + 3) & ~3) * 4u;
+        const uint32_t bar = smem_u32(bars + slot);
+        const uint32_t dst = smem_u32(sl + 4);
         mbar_expect_tx(bar, 5u * bytes);
-        bulk_g2s(dst, g.uv + p0, bytes, bar);
-        bulk_g2s(dst + SPB_CAP * 4, g.logd + p0, bytes, bar);
-        bulk_g2s(dst + 2 * SPB_CAP * 4, pr.src_rgb + p0, bytes, bar);
-        bulk_g2s(dst + 3 * SPB_CAP * 4, pr.src_rgb + (size_t)g.n_pad + p0, bytes, bar);
-        bulk_g2s(dst + 4 * SPB_CAP * 4, pr.src_rgb + 2 * (size_t)g.n_pad + p0, bytes, bar);
+        bulk_g2s(dst, g.uv + td.y, bytes, bar);
+        bulk_g2s(dst + SPB_TILE * 4, g.logd + td.y, bytes, bar);
+        bulk_g2s(dst + 2 * SPB_TILE * 4, pr.src_rgb + td.y, bytes, bar);
+        bulk_g2s(dst + 3 * SPB_TILE * 4, pr.src_rgb + plane + td.y, bytes, bar);
+        bulk_g2s(dst + 4 * SPB_TILE * 4, pr.src_rgb + 2 * plane + td.y, bytes, bar);
     };
-    if (threadIdx.x == 0) {
+
+    int4 td_pref = make_int4(0, 0, 0, 0);
+    if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < SPB_STAGES - 1; ++s) {
-            const int ch = blockIdx.x + s * G;
-            if (ch < nchunks) issue(ch, s);
+        for (int s = 0; s < SPB_WSTAGES - 1; ++s) {
+            const int t = t_first + s * WS;
+            if (t < g.n_tiles) issue(__ldg(tiles + t), s);
         }
+        const int tp = t_first + (SPB_WSTAGES - 1) * WS;
+        if (tp < g.n_tiles) td_pref = __ldg(tiles + tp);
     }
 
     const float4* trg = reinterpret_cast<const float4*>(pr.trg_rgba);
-    const int Wl = pr.Wl, Hl = pr.Hl;
-    PointOut po{nullptr, 0, g.n_pts};
+    const int Wl = pr.Wl;
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
 
-    int it = 0;
-    for (int ch = blockIdx.x; ch < nchunks; ch += G, ++it) {
-        const int slot = it % SPB_STAGES;
-        __syncthreads();                                   // every warp is done with the slot refilled below
-        if (threadIdx.x == 0) {
-            const int nx = ch + (SPB_STAGES - 1) * G;
-            if (nx < nchunks) issue(nx, (it + SPB_STAGES - 1) % SPB_STAGES);
+    int slot = 0, fill = SPB_WSTAGES - 1;                  // slot consumed now / slot refilled now
+    uint32_t phase = 0;
+    for (int t = t_first; t < g.n_tiles; t += WS) {
+        if (lane == 0) {
+            const int tn = t + (SPB_WSTAGES - 1) * WS;
+            if (tn < g.n_tiles) issue(td_pref, fill);
+            const int tp = tn + WS;
+            if (tp < g.n_tiles) td_pref = __ldg(tiles + tp);
         }
-        mbar_wait(smem_u32(s_bar + slot), (uint32_t)((it / SPB_STAGES) & 1));
-        const int t = ch * SPB_WARPS + warp;
-        if (t < g.n_tiles) {
-            const int p0 = __ldg(&tiles[ch * SPB_WARPS].y);
-            const int4 td = __ldg(tiles + t);
-            const int cnt = td.z;
-            const uint32_t* st_uv = s_dyn + slot * SPB_STAGE_WORDS + (td.y - p0);
-            const float* st_l = reinterpret_cast<const float*>(st_uv) + SPB_CAP;
-            const float shift = __ldg(pr.k + td.x) - __ldg(g.seg_lkp + td.x);
-            float seg[NSEG];
+        __syncwarp();
+        mbar_wait(smem_u32(bars + slot), phase);
+        const uint32_t* sl = ring + slot * SPB_SLOT_WORDS;
+        const int sidx = (int)sl[0], cnt = (int)sl[1];
+        const float shift = (sidx < SPB_NSHIFT) ? s_shift[sidx] : (__ldg(pr.k + sidx) - __ldg(g.seg_lkp + sidx));
+        const uint32_t* s_uv = sl + 4;
+        const float* s_f = reinterpret_cast<const float*>(sl + 4);
+        float seg[NSEG];
 #pragma unroll
-            for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
+        for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
 #pragma unroll
-            for (int j = 0; j < SPB_PPT; ++j) {
-                const int i = j * 32 + lane;
-                if (i < cnt) {
-                    const uint32_t w = st_uv[i];
-                    const float u = (float)(w & 0xffffu);
-                    const float v = (float)((w >> 16) & 0x7fffu);
-                    const float z = __expf(st_l[i] + shift);
-                    const float Xx = (u - c[C_CX]) * z * c[C_IFX];
-                    const float Xy = (v - c[C_CY]) * z * c[C_IFY];
-                    const bool sok = (w >> 31) && (z > 1e-7f);
-                    eval_point<MODE, NP, false, NACC, NSEG>(c, trg, Wl, Hl, Xx, Xy, z, sok, st_l[SPB_CAP + i],
-                                                            st_l[2 * SPB_CAP + i], st_l[3 * SPB_CAP + i], irls_eps,
-                                                            acc, seg, po, 0);
+        for (int j = 0; j < SPB_PPT; ++j) {
+            const int i = j * 32 + lane;
+            if (i < cnt) {
+                Proj q;
+                if (project_point(c, s_uv[i], s_f[SPB_TILE + i], shift, Wl, q)) {
+                    const float i0 = s_f[2 * SPB_TILE + i], i1 = s_f[3 * SPB_TILE + i], i2 = s_f[4 * SPB_TILE + i];
+                    if constexpr (MODE == MODE_GRAD)
+                        point_grad<AFF>(c, trg, Wl, q, i0, i1, i2, acc, seg[0]);
+                    else
+                        point_gn<NP, NACC, NSEG>(c, trg, Wl, q, i0, i1, i2, irls_eps, acc, seg);
                 }
             }
-            tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
         }
+        tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
+        __syncwarp();                                      // every lane is done with this slot
+        fill = slot;
+        if (++slot == SPB_WSTAGES) { slot = 0; phase ^= 1u; }
     }
     __syncthreads();
     block_reduce_store<NACC>(acc, s_red, part_pair + (size_t)blockIdx.x * NACC);
@@ -501,11 +471,17 @@ struct PairPack {
 
 // occupancy target: 3 CTAs/SM (<= 80 registers) for the gradient kernel, 2 for the GN kernel whose
 // 38 accumulators do not fit 80 registers without spilling
+#ifndef SPB_OCC_GRAD
+#define SPB_OCC_GRAD 3
+#endif
+#ifndef SPB_OCC_GN
+#define SPB_OCC_GN 2
+#endif
 template <int MODE>
-struct Occ { static constexpr int CTAS = (MODE == MODE_GRAD) ? 3 : 2; };
+struct Occ { static constexpr int CTAS = (MODE == MODE_GRAD) ? SPB_OCC_GRAD : SPB_OCC_GN; };
 
 // B pairs over one geometry, descriptors by value (Python per-call path: no descriptor upload)
-template <int MODE, int NP>
+template <int MODE, int NP, bool AFF>
 __global__ void __launch_bounds__(SPB_THREADS, Occ<MODE>::CTAS)
 k_align_inline(const __grid_constant__ SpbGeom g, const __grid_constant__ PairPack pack, float irls_eps,
                float* __restrict__ work) {
@@ -514,7 +490,7 @@ k_align_inline(const __grid_constant__ SpbGeom g, const __grid_constant__ PairPa
     const int pair = blockIdx.y;
     const size_t stride = (size_t)gridDim.x * NACC + (size_t)g.n_tiles * NSEG;
     float* base = work + pair * stride;
-    align_body_staged<MODE, NP>(g, pack.p[pair], irls_eps, base, base + (size_t)gridDim.x * NACC);
+    align_body_warp<MODE, NP, AFF>(g, pack.p[pair], irls_eps, base, base + (size_t)gridDim.x * NACC);
 }
 
 // same, slow path that also materialises the per-point statistics (register-prefetch body)
@@ -530,7 +506,7 @@ k_align_stats(const __grid_constant__ SpbGeom g, const __grid_constant__ PairPac
 }
 
 // n_pairs independent problems, descriptors in device memory (batched solver / benchmark path)
-template <int MODE, int NP>
+template <int MODE, int NP, bool AFF>
 __global__ void __launch_bounds__(SPB_THREADS, Occ<MODE>::CTAS)
 k_align_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs, float irls_eps,
                float* __restrict__ work, int64_t work_stride) {
@@ -544,14 +520,23 @@ k_align_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pa
     }
     __syncthreads();
     float* base = work + pair * work_stride;
-    align_body_staged<MODE, NP>(s_g, s_pr, irls_eps, base, base + (size_t)gridDim.x * NACC);
+    align_body_warp<MODE, NP, AFF>(s_g, s_pr, irls_eps, base, base + (size_t)gridDim.x * NACC);
 }
 
 // ------------------------------------------------------------------------------------------------
 // finalize: fixed-order reduction of the partials
 // ------------------------------------------------------------------------------------------------
-__global__ void k_finalize_grad(const __grid_constant__ SpbGeom g, int ctas, const float* __restrict__ work,
-                                float* __restrict__ out_pair, float* __restrict__ out_gk) {
+// `scale_cols`: the hot path accumulates d cost / d M with M = R diag(1/fx, 1/fy, 1); d cost / d R scales
+// the first two columns by 1/fx, 1/fy.  (The statistics path accumulates d cost / d R directly.)
+__device__ __forceinline__ float grad_col_scale(int idx, const float* K, bool scale_cols) {
+    if (!scale_cols || idx < 4 || idx > 12) return 1.0f;
+    const int col = (idx - 4) % 3;
+    return col == 0 ? 1.0f / K[0] : (col == 1 ? 1.0f / K[4] : 1.0f);
+}
+
+__global__ void k_finalize_grad(const __grid_constant__ SpbGeom g, int ctas, int scale_cols,
+                                const float* __restrict__ work, float* __restrict__ out_pair,
+                                float* __restrict__ out_gk) {
     const int pair = blockIdx.x;
     const size_t stride = (size_t)ctas * SPB_PAIR_NOUT + (size_t)g.n_tiles;
     const float* pp = work + pair * stride;
@@ -560,6 +545,7 @@ __global__ void k_finalize_grad(const __grid_constant__ SpbGeom g, int ctas, con
     if (threadIdx.x < SPB_PAIR_NOUT) {
         float v = 0.f;
         for (int cta = 0; cta < ctas; ++cta) v += pp[(size_t)cta * SPB_PAIR_NOUT + threadIdx.x];
+        v *= grad_col_scale(threadIdx.x, g.K, scale_cols != 0);
         out_pair[pair * SPB_PAIR_NOUT + threadIdx.x] = (threadIdx.x == 15) ? v : v * norm;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -696,18 +682,18 @@ __global__ void k_finalize_points(int ctas, int P, const float* __restrict__ wor
 // host-side launch helpers (C ABI)
 // ------------------------------------------------------------------------------------------------
 static inline int ctas_for(int n_tiles, int n_pairs) {
-    // a CTA streams chunks of SPB_WARPS tiles; aim at ~4 waves of 3 CTAs/SM over all pairs so the
-    // tail wave is small, but never more CTAs than chunks
-    const int nchunks = (n_tiles + SPB_WARPS - 1) / SPB_WARPS;
+    // every warp streams a strided set of tiles through its own ring; aim at ~4 waves of 3 CTAs/SM over
+    // all pairs so the tail wave is small, but keep >= 2 tiles per warp when there is enough work
+    const int max_ctas = (n_tiles + SPB_WARPS - 1) / SPB_WARPS;
     int want = (148 * 3 * 4 + n_pairs - 1) / (n_pairs > 0 ? n_pairs : 1);
-    if (want > nchunks) want = nchunks;
+    if (want > max_ctas) want = max_ctas;
     if (want < 1) want = 1;
     return want;
 }
 
 template <typename K>
 static inline cudaError_t allow_dyn_smem(K kernel) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_DYN_SMEM);
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_FAST_DYN_SMEM);
 }
 
 static inline int ctas_for_points(int P) {
@@ -744,12 +730,20 @@ extern "C" int spb_cost_grad(const SpbGeom* geom, const SpbPair* pairs, int B, f
     if (stats) {
         k_align_stats<<<grid, SPB_THREADS, 0, st>>>(*geom, pack, work, *stats);
     } else {
-        cudaError_t e = allow_dyn_smem(k_align_inline<MODE_GRAD, 6>);
-        if (e != cudaSuccess) return (int)e;
-        k_align_inline<MODE_GRAD, 6><<<grid, SPB_THREADS, SPB_DYN_SMEM, st>>>(*geom, pack, 0.f, work);
+        bool aff = false;
+        for (int j = 0; j < B; ++j) aff = aff || (pairs[j].aff_src != nullptr && pairs[j].aff_trg != nullptr);
+        if (aff) {
+            cudaError_t e = allow_dyn_smem(k_align_inline<MODE_GRAD, 6, true>);
+            if (e != cudaSuccess) return (int)e;
+            k_align_inline<MODE_GRAD, 6, true><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(*geom, pack, 0.f, work);
+        } else {
+            cudaError_t e = allow_dyn_smem(k_align_inline<MODE_GRAD, 6, false>);
+            if (e != cudaSuccess) return (int)e;
+            k_align_inline<MODE_GRAD, 6, false><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(*geom, pack, 0.f, work);
+        }
     }
     SPB_CHECK_LAUNCH();
-    k_finalize_grad<<<B, 256, 0, st>>>(*geom, ctas, work, out_pair, out_gk);
+    k_finalize_grad<<<B, 256, 0, st>>>(*geom, ctas, stats ? 0 : 1, work, out_pair, out_gk);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
@@ -783,16 +777,16 @@ extern "C" int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, con
     dim3 grid(ctas, n_pairs);
     if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
     if (with_affine) {
-        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GN, 8>);
+        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GN, 8, true>);
         if (e != cudaSuccess) return (int)e;
-        k_align_global<MODE_GN, 8><<<grid, SPB_THREADS, SPB_DYN_SMEM, st>>>(geoms, pairs, irls_eps, work, work_stride);
+        k_align_global<MODE_GN, 8, true><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, irls_eps, work, work_stride);
         SPB_CHECK_LAUNCH();
         if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
         k_finalize_gn<8><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
     } else {
-        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GN, 6>);
+        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GN, 6, true>);
         if (e != cudaSuccess) return (int)e;
-        k_align_global<MODE_GN, 6><<<grid, SPB_THREADS, SPB_DYN_SMEM, st>>>(geoms, pairs, irls_eps, work, work_stride);
+        k_align_global<MODE_GN, 6, true><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, irls_eps, work, work_stride);
         SPB_CHECK_LAUNCH();
         if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
         k_finalize_gn<6><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
@@ -813,6 +807,7 @@ __global__ void k_finalize_grad_global(const SpbGeom* __restrict__ geoms, const 
     if (threadIdx.x < SPB_PAIR_NOUT) {
         float v = 0.f;
         for (int cta = 0; cta < ctas; ++cta) v += pp[(size_t)cta * SPB_PAIR_NOUT + threadIdx.x];
+        v *= grad_col_scale(threadIdx.x, g.K, true);
         out_pair[pair * SPB_PAIR_NOUT + threadIdx.x] = (threadIdx.x == 15) ? v : v * norm;
     }
     const int so = seg_off[pair];
@@ -827,8 +822,8 @@ __global__ void k_finalize_grad_global(const SpbGeom* __restrict__ geoms, const 
 }
 
 extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, int n_pairs,
-                                   int max_tiles, float* work, int64_t work_stride, float* out_pair, float* out_gk,
-                                   void* ev_before, void* ev_after, void* stream) {
+                                   int max_tiles, int with_affine, float* work, int64_t work_stride, float* out_pair,
+                                   float* out_gk, void* ev_before, void* ev_after, void* stream) {
     if (!geoms || !pairs || !seg_off || n_pairs < 1 || max_tiles < 1 || !work || !out_pair || !out_gk)
         return SPB_EINVAL;
     if (n_pairs > 65535) return SPB_ELIMIT;
@@ -837,9 +832,15 @@ extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, c
     if (work_stride < (int64_t)ctas * SPB_PAIR_NOUT + max_tiles) return SPB_EINVAL;
     dim3 grid(ctas, n_pairs);
     if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
-    cudaError_t e = allow_dyn_smem(k_align_global<MODE_GRAD, 6>);
-    if (e != cudaSuccess) return (int)e;
-    k_align_global<MODE_GRAD, 6><<<grid, SPB_THREADS, SPB_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
+    if (with_affine) {
+        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GRAD, 6, true>);
+        if (e != cudaSuccess) return (int)e;
+        k_align_global<MODE_GRAD, 6, true><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
+    } else {
+        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GRAD, 6, false>);
+        if (e != cudaSuccess) return (int)e;
+        k_align_global<MODE_GRAD, 6, false><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
+    }
     SPB_CHECK_LAUNCH();
     if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
     k_finalize_grad_global<<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_gk);

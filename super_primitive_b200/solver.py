@@ -82,6 +82,7 @@ class AlignmentBatch:
                                     for p in problems]).contiguous()
         self._keep = [(p['src_rgb'], p['trg_rgba']) for p in problems]
         use_aff = self.with_affine or any(p.get('aff_src') is not None for p in problems)
+        self.use_affine = use_aff
         # descriptor arrays
         garr = (nat.SpbGeom * len(geoms))()
         for i, g in enumerate(geoms):
@@ -151,6 +152,7 @@ class AlignmentBatch:
         e0, e1 = (None, None) if ev is None else (ev[0].cuda_event, ev[1].cuda_event)
         nat.check(nat.lib().spb_grad_accumulate(self.d_geoms.data_ptr(), self.d_pairs.data_ptr(),
                                                 self.d_seg_off.data_ptr(), self.n, self.max_tiles,
+                                                1 if self.use_affine else 0,
                                                 self.work.data_ptr(), self.work_stride, self.out_pair.data_ptr(),
                                                 self.out_gk.data_ptr(), e0, e1, _stream()), "spb_grad_accumulate")
         self.launches += 2

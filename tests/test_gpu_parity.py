@@ -255,3 +255,40 @@ def test_cpu_tensors_fail_loudly():
     g = Golden("tiny_strips", "cpu")
     with pytest.raises(RuntimeError):
         do.photomeric_cost(g.src(0), g.trg(0), g.k(), g.poses()[0], CFG0)
+
+
+@pytest.mark.parametrize("case", STATS_CASES)
+@pytest.mark.parametrize("mode", ["median", "mean"])
+def test_segment_depth_reinit(case, mode):
+    """odometery/depth_init.py:10-67 -- per-segment (lower) median / mean re-initialisation."""
+    from super_primitive_b200.depth_init import segment_based_depth_reinit
+    g = Golden(case, "cuda")
+    src = g.src(g.n_levels - 1)
+    est = g.t("reinit_est_depth").clone()
+    k, vis = segment_based_depth_reinit(est, src, mode, return_info=True)
+    torch.set_grad_enabled(True)
+    assert np.array_equal(to_np(vis), g.z["reinit_visible"])
+    assert_close(to_np(k), g.z[f"reinit_{mode}"], 1e-5, f"reinit {mode}")
+    assert float(est.min()) >= 1e-6          # invalid entries clamped in place like the reference
+    # numpy input + default return signature
+    k2 = segment_based_depth_reinit(g.z["reinit_est_depth"].copy(), src, mode)
+    torch.set_grad_enabled(True)
+    assert_close(to_np(k2), g.z[f"reinit_{mode}"], 1e-5, "numpy input")
+
+
+def test_segment_depth_reinit_large_segments():
+    """Segments far larger than one CTA pass (C1 shape) against the CPU oracle."""
+    from oracle import ref_port as port
+    from super_primitive_b200 import synthetic as syn
+    from super_primitive_b200.depth_init import segment_based_depth_reinit
+    src = syn.make_keyframe(192, 256, 8, kind="overlap", seed=5, noise=0.01)
+    gen = torch.Generator().manual_seed(3)
+    est = 1.5 + torch.rand((192, 256), generator=gen)
+    est[torch.rand((192, 256), generator=gen) < 0.3] = 0.0          # 30 % holes
+    est[:, :40] = 0.0                                                # segment 0 mostly invisible
+    for mode in ("median", "mean"):
+        ref, vis = port.segment_median_reinit(est.clone(), src, mode)
+        k, v = segment_based_depth_reinit(est.clone().cuda(), src.to("cuda"), mode, return_info=True)
+        torch.set_grad_enabled(True)
+        assert np.array_equal(to_np(v), to_np(vis))
+        assert_close(to_np(k), to_np(ref), 1e-5, mode)
