@@ -442,20 +442,54 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
         float seg[NSEG];
 #pragma unroll
         for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
+        auto consume = [&](const Proj& q, const Taps4& tp, bool ok, int i) {
+            if (ok) {
+                const float i0 = s_f[2 * SPB_TILE + i], i1 = s_f[3 * SPB_TILE + i], i2 = s_f[4 * SPB_TILE + i];
+                if constexpr (MODE == MODE_GRAD)
+                    point_grad<AFF>(c, tp, q, i0, i1, i2, acc, seg[0]);
+                else
+                    point_gn<NP, NACC, NSEG>(c, tp, q, i0, i1, i2, irls_eps, acc, seg);
+            }
+        };
+#if SPB_PIPE == 2
+        // software pipeline: the taps of point j+1 are requested before point j is consumed, so every
+        // lane keeps two gathers in flight (the target image is the only operand not staged by TMA)
+        Proj qa, qb;
+        Taps4 ta, tb;
+        bool oka = false, okb = false;
+        if (lane < cnt) {
+            oka = project_point(c, s_uv[lane], s_f[SPB_TILE + lane], shift, Wl, qa);
+            load_taps(trg, Wl, qa.off, ta);
+        }
+#pragma unroll
+        for (int j = 0; j < SPB_PPT; j += 2) {
+            const int i0 = j * 32 + lane, i1 = i0 + 32, i2 = i0 + 64;
+            okb = false;
+            if (i1 < cnt) {
+                okb = project_point(c, s_uv[i1], s_f[SPB_TILE + i1], shift, Wl, qb);
+                load_taps(trg, Wl, qb.off, tb);
+            }
+            consume(qa, ta, oka, i0);
+            oka = false;
+            if (j + 2 < SPB_PPT && i2 < cnt) {
+                oka = project_point(c, s_uv[i2], s_f[SPB_TILE + i2], shift, Wl, qa);
+                load_taps(trg, Wl, qa.off, ta);
+            }
+            consume(qb, tb, okb, i1);
+        }
+#else
 #pragma unroll
         for (int j = 0; j < SPB_PPT; ++j) {
             const int i = j * 32 + lane;
             if (i < cnt) {
                 Proj q;
-                if (project_point(c, s_uv[i], s_f[SPB_TILE + i], shift, Wl, q)) {
-                    const float i0 = s_f[2 * SPB_TILE + i], i1 = s_f[3 * SPB_TILE + i], i2 = s_f[4 * SPB_TILE + i];
-                    if constexpr (MODE == MODE_GRAD)
-                        point_grad<AFF>(c, trg, Wl, q, i0, i1, i2, acc, seg[0]);
-                    else
-                        point_gn<NP, NACC, NSEG>(c, trg, Wl, q, i0, i1, i2, irls_eps, acc, seg);
-                }
+                Taps4 tp;
+                const bool ok = project_point(c, s_uv[i], s_f[SPB_TILE + i], shift, Wl, q);
+                if (ok) load_taps(trg, Wl, q.off, tp);
+                consume(q, tp, ok, i);
             }
         }
+#endif
         tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
         __syncwarp();                                      // every lane is done with this slot
         fill = slot;
@@ -472,7 +506,7 @@ struct PairPack {
 // occupancy target: 3 CTAs/SM (<= 80 registers) for the gradient kernel, 2 for the GN kernel whose
 // 38 accumulators do not fit 80 registers without spilling
 #ifndef SPB_OCC_GRAD
-#define SPB_OCC_GRAD 3
+#define SPB_OCC_GRAD (SPB_PIPE == 2 ? 2 : 3)
 #endif
 #ifndef SPB_OCC_GN
 #define SPB_OCC_GN 2

@@ -17,6 +17,9 @@
 #pragma once
 #include "spb_common.cuh"
 
+#ifndef SPB_PIPE
+#define SPB_PIPE 2                             // points per lane whose taps are in flight (1 or 2)
+#endif
 #ifndef SPB_WSTAGES
 #define SPB_WSTAGES 3                          // ring slots per warp
 #endif
@@ -127,19 +130,27 @@ __device__ __forceinline__ bool project_point(const float* __restrict__ c, uint3
     const float fxf = floorf(ix), fyf = floorf(iy);
     q.fx = ix - fxf;
     q.fy = iy - fyf;
-    q.off = (int)fyf * Wl + (int)fxf;
+    q.off = ok ? ((int)fyf * Wl + (int)fxf) : 0;                   // invalid points load texel 0 (never used)
     return ok;
+}
+
+// the four RGBA taps of one point; issued early (software pipelining), consumed by point_grad / point_gn
+struct Taps4 {
+    float4 nw, ne, sw, se;
+};
+__device__ __forceinline__ void load_taps(const float4* __restrict__ trg, int Wl, int off, Taps4& t) {
+    const float4* p0 = trg + off;
+    t.nw = __ldg(p0); t.ne = __ldg(p0 + 1); t.sw = __ldg(p0 + Wl); t.se = __ldg(p0 + Wl + 1);
 }
 
 // ---- gradient mode --------------------------------------------------------------------------------
 // acc[16] = cost, gt[3], gM[9] (d cost / d M; the finalize kernel scales columns by 1/fx, 1/fy to get
 //           d cost / d R), ga, gb, nvalid ; gk = d cost / d k of the tile's segment
 template <bool AFF>
-__device__ __forceinline__ void point_grad(const float* __restrict__ c, const float4* __restrict__ trg, int Wl,
+__device__ __forceinline__ void point_grad(const float* __restrict__ c, const Taps4& tp,
                                            const Proj& q, float Is0, float Is1, float Is2,
                                            float (&acc)[16], float& gk) {
-    const float4* p0 = trg + q.off;
-    const float4 nw = __ldg(p0), ne = __ldg(p0 + 1), sw = __ldg(p0 + Wl), se = __ldg(p0 + Wl + 1);
+    const float4 nw = tp.nw, ne = tp.ne, sw = tp.sw, se = tp.se;
     float I[3], dx[3], dy[3];
     blend(nw.x, ne.x, sw.x, se.x, q.fx, q.fy, I[0], dx[0], dy[0]);
     blend(nw.y, ne.y, sw.y, se.y, q.fx, q.fy, I[1], dx[1], dy[1]);
@@ -175,11 +186,10 @@ __device__ __forceinline__ void point_grad(const float* __restrict__ c, const fl
 // acc layout = upper triangle of the NPxNP pose block (row-major packed), g_p[NP], cost, wcost, nvalid
 // seg layout = B column [NP], D, g_d
 template <int NP, int NACC, int NSEG>
-__device__ __forceinline__ void point_gn(const float* __restrict__ c, const float4* __restrict__ trg, int Wl,
+__device__ __forceinline__ void point_gn(const float* __restrict__ c, const Taps4& tp,
                                          const Proj& q, float Is0, float Is1, float Is2, float irls_eps,
                                          float (&acc)[NACC], float (&seg)[NSEG]) {
-    const float4* p0 = trg + q.off;
-    const float4 nw = __ldg(p0), ne = __ldg(p0 + 1), sw = __ldg(p0 + Wl), se = __ldg(p0 + Wl + 1);
+    const float4 nw = tp.nw, ne = tp.ne, sw = tp.sw, se = tp.se;
     float I[3], dx[3], dy[3];
     blend(nw.x, ne.x, sw.x, se.x, q.fx, q.fy, I[0], dx[0], dy[0]);
     blend(nw.y, ne.y, sw.y, se.y, q.fx, q.fy, I[1], dx[1], dy[1]);

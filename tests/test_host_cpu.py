@@ -1,0 +1,146 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares (no compute without a GPU), module aliasing for the reference's callers, the lazy statistics
+dictionary, the synthetic generator and the pyramid semantics."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    txt = open(os.path.join(ROOT, "include", "spb200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:int|int64_t)\s+(spb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from super_primitive_b200 import _native
+    if not os.path.exists(_native.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    names = _declared_functions()
+    assert len(names) >= 18
+    handle = ctypes.CDLL(_native.LIB_PATH)
+    missing = [n for n in names if not hasattr(handle, n)]
+    assert not missing, f"declared in include/spb200.h but not exported: {missing}"
+    # and the Python binding covers the same set
+    assert set(names) == set(_native.EXPORTS), set(names) ^ set(_native.EXPORTS)
+    assert _native.lib().spb_version() >= 100
+
+
+def test_struct_layouts_match_header_sizes():
+    from super_primitive_b200 import _native
+    assert ctypes.sizeof(_native.SpbGeom) == 6 * 8 + 6 * 4
+    assert ctypes.sizeof(_native.SpbPair) == 7 * 8 + 4 * 4
+    assert ctypes.sizeof(_native.SpbStats) == 8 * 8
+
+
+def test_argument_validation_without_gpu():
+    """Entry points reject bad arguments before touching the device."""
+    from super_primitive_b200 import _native
+    lib = _native.lib()
+    assert lib.spb_compact_count(None, 1, 4, 4, None, None) == -1
+    assert lib.spb_pack_rgba(None, 0, 1, 4, 4, None, None) == -1
+    assert lib.spb_cost_grad(None, None, 1, None, None, None, None, None) == -1
+    assert lib.spb_gn_accumulate(None, None, None, 1, 1, 1e-3, 0, None, 0, None, None, None, None, None) == -1
+    assert lib.spb_segment_reinit(None, None, 1, None, None, None, None, None) == -1
+
+
+def test_install_as_core_aliases_modules():
+    import super_primitive_b200 as spb
+    saved = {k: v for k, v in sys.modules.items() if k == "core" or k.startswith("core.")}
+    try:
+        spb.install_as_core()
+        import core.dense_optim as do
+        import core.dense_optim_batch as dob
+        import core.depth_render as dr
+        import core.ops as ops
+        for fn in ("photomeric_cost", "photomeric_cost_precomputed", "unproject_kf", "unproject_kf_to_depths",
+                   "transform_points", "project_points"):
+            assert callable(getattr(do, fn)), fn
+        assert callable(dob.photomeric_cost_batch) and callable(dr.estimate_depth_kf_native)
+        assert callable(ops.project_points_batch) and callable(ops.transform_points_batch)
+    finally:
+        for k in [k for k in sys.modules if k == "core" or k.startswith("core.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_signatures_match_reference_call_surface():
+    import inspect
+    from super_primitive_b200 import dense_optim as do, dense_optim_batch as dob, depth_render as dr, depth_init as di
+    sig = lambda f: list(inspect.signature(f).parameters)   # noqa: E731
+    assert sig(do.photomeric_cost) == ['src_keyframe', 'trg_keyframe', 'src_keypoint_logdepth', 'pose', 'cost_config',
+                                       'affine_comp']
+    assert sig(do.photomeric_cost_precomputed) == ['src_precomputed', 'trg_keyframe', 'pose', 'cost_config',
+                                                   'affine_comp']
+    assert sig(dob.photomeric_cost_batch) == ['src_keyframe', 'trg_images', 'trg_Ks', 'src_keypoint_logdepth', 'poses',
+                                              'cost_config', 'affine_comp']
+    assert sig(do.unproject_kf) == ['kf', 'keypoint_logdepth', 'jacobian']
+    assert sig(do.unproject_kf_to_depths) == ['kf', 'keypoint_logdepth']
+    assert sig(dr.estimate_depth_kf_native) == ['kf', 'kf_logdepth', 'pose', 'mean']
+    assert sig(di.segment_based_depth_reinit) == ['estimated_depth', 'kf', 'mode', 'return_info']
+
+
+def test_cpu_tensors_are_refused():
+    from super_primitive_b200 import dense_optim as do, synthetic as syn
+    src, trg, k0, pose0 = syn.two_frame_problem(16, 24, 2)
+    with pytest.raises(RuntimeError):
+        do.photomeric_cost(src, trg, k0, pose0, {'mode': 'colour', 'collect_stats': 0})
+    with pytest.raises(NotImplementedError):
+        do.photomeric_cost(src, trg, k0, pose0, {'mode': 'colour_norm', 'collect_stats': 0})
+
+
+def test_lazy_result_materialises_once():
+    from super_primitive_b200.dense_optim import LazyResult
+    calls = []
+
+    def produce():
+        calls.append(1)
+        return {'a': 1, 'median_depth': None}
+
+    r = LazyResult(torch.zeros(1), produce)
+    assert r['residual'].shape == (1,) and calls == []
+    assert 'residual' in r and calls == []
+    assert r['a'] == 1 and calls == [1]
+    assert set(r.keys()) == {'residual', 'a', 'median_depth'} and len(r) == 3 and calls == [1]
+    assert r.get('median_depth', 5) is None
+    assert dict(r.items())['a'] == 1 and calls == [1]
+
+
+def test_synthetic_generator_contract():
+    from super_primitive_b200 import synthetic as syn
+    for kind in ("strips", "overlap", "rects"):
+        kf = syn.make_keyframe(48, 64, 6, kind=kind, seed=2)
+        assert kf.image.shape == (3, 48, 64) and kf.keypoint_regions.shape == (6, 48, 64)
+        assert kf.keypoint_regions.dtype == torch.bool and kf.logdepth_perseg.shape == (6, 48, 64)
+        assert torch.all(kf.logdepth_perseg[~kf.keypoint_regions] == 0)
+        rc = (0.5 * (torch.tensor([48., 64.]) - 1) * (kf.keypoints + 1)).round().long()
+        assert all(bool(kf.keypoint_regions[b, rc[b, 0], rc[b, 1]]) for b in range(6)), kind
+        assert kf.keypoint_regions.flatten(1).any(1).all()
+    strips = syn.make_keyframe(48, 64, 8, kind="strips").keypoint_regions
+    assert int(strips.sum()) == 48 * 64 and int(strips.sum(0).max()) == 1     # exact partition
+    a = syn.make_keyframe(32, 40, 4, kind="rects", seed=9, noise=0.02)
+    b = syn.make_keyframe(32, 40, 4, kind="rects", seed=9, noise=0.02)
+    assert torch.equal(a.image, b.image) and torch.equal(a.keypoint_regions, b.keypoint_regions)
+
+
+def test_pyramid_matches_reference_semantics():
+    """3x3 [1 2 1]^2/16 blur with reflect padding then [::2, ::2]; geometry untouched (geo_down=False)."""
+    from super_primitive_b200 import synthetic as syn
+    kf = syn.make_keyframe(32, 48, 3, kind="strips", noise=0.01, seed=1)
+    pyr = syn.keyframe_pyramid(kf, 0, 3)
+    assert [tuple(p.image.shape[1:]) for p in pyr] == [(8, 12), (16, 24), (32, 48)]
+    assert all(p.logdepth_perseg is kf.logdepth_perseg and p.keypoint_regions is kf.keypoint_regions for p in pyr)
+    img = kf.image.double().numpy()
+    pad = np.pad(img, ((0, 0), (1, 1), (1, 1)), mode="reflect")
+    ker = np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]]) / 16.0
+    blur = sum(ker[i, j] * pad[:, i:i + 32, j:j + 48] for i in range(3) for j in range(3))
+    assert np.allclose(pyr[1].image.numpy(), blur[:, ::2, ::2], atol=1e-6)
+    assert torch.allclose(pyr[0].K_img[0, 0], kf.K[0, 0] * 0.25)
