@@ -358,6 +358,7 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
 }
 
 #include "spb_fast.cuh"
+#include "spb_gn_packed.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Hot-path body: per-warp bulk-async pipelines (see spb_fast.cuh).  grid = (ctas_per_pair, pairs)
@@ -419,9 +420,12 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
 
     const float4* trg = reinterpret_cast<const float4*>(pr.trg_rgba);
     const int Wl = pr.Wl;
+    constexpr bool PACKED = (MODE == MODE_GN && NP == 6);   // FFMA2 formulation (spb_gn_packed.cuh)
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+    GnAcc6 pacc;
+    pacc.zero();
 
     int slot = 0, fill = SPB_WSTAGES - 1;                  // slot consumed now / slot refilled now
     uint32_t phase = 0;
@@ -442,11 +446,15 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
         float seg[NSEG];
 #pragma unroll
         for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
+        GnSeg6 pseg;
+        pseg.zero();
         auto consume = [&](const Proj& q, const Taps4& tp, bool ok, int i) {
             if (ok) {
                 const float i0 = s_f[2 * SPB_TILE + i], i1 = s_f[3 * SPB_TILE + i], i2 = s_f[4 * SPB_TILE + i];
                 if constexpr (MODE == MODE_GRAD)
                     point_grad<AFF>(c, tp, q, i0, i1, i2, acc, seg[0]);
+                else if constexpr (PACKED)
+                    point_gn6_packed(c, tp, q, i0, i1, i2, irls_eps, pacc, pseg);
                 else
                     point_gn<NP, NACC, NSEG>(c, tp, q, i0, i1, i2, irls_eps, acc, seg);
             }
@@ -490,11 +498,13 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
             }
         }
 #endif
+        if constexpr (PACKED) pseg.store(seg);
         tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
         __syncwarp();                                      // every lane is done with this slot
         fill = slot;
         if (++slot == SPB_WSTAGES) { slot = 0; phase ^= 1u; }
     }
+    if constexpr (PACKED) pacc.store(acc);
     __syncthreads();
     block_reduce_store<NACC>(acc, s_red, part_pair + (size_t)blockIdx.x * NACC);
 }
@@ -506,17 +516,19 @@ struct PairPack {
 // occupancy target: 3 CTAs/SM (<= 80 registers) for the gradient kernel, 2 for the GN kernel whose
 // 38 accumulators do not fit 80 registers without spilling
 #ifndef SPB_OCC_GRAD
-#define SPB_OCC_GRAD (SPB_PIPE == 2 ? 2 : 3)
+#define SPB_OCC_GRAD (SPB_PIPE == 2 ? 2 : 4)
 #endif
 #ifndef SPB_OCC_GN
-#define SPB_OCC_GN 2
+#define SPB_OCC_GN (SPB_PIPE == 2 ? 2 : 3)
 #endif
-template <int MODE>
-struct Occ { static constexpr int CTAS = (MODE == MODE_GRAD) ? SPB_OCC_GRAD : SPB_OCC_GN; };
+template <int MODE, int NP>
+struct Occ {   // the 8-column (affine) GN variant keeps 47 accumulators: 2 CTAs/SM, no spills
+    static constexpr int CTAS = (MODE == MODE_GRAD) ? SPB_OCC_GRAD : (NP == 8 ? 2 : SPB_OCC_GN);
+};
 
 // B pairs over one geometry, descriptors by value (Python per-call path: no descriptor upload)
 template <int MODE, int NP, bool AFF>
-__global__ void __launch_bounds__(SPB_THREADS, Occ<MODE>::CTAS)
+__global__ void __launch_bounds__(SPB_THREADS, Occ<MODE, NP>::CTAS)
 k_align_inline(const __grid_constant__ SpbGeom g, const __grid_constant__ PairPack pack, float irls_eps,
                float* __restrict__ work) {
     constexpr int NACC = Sizes<MODE, NP>::NACC;
@@ -541,7 +553,7 @@ k_align_stats(const __grid_constant__ SpbGeom g, const __grid_constant__ PairPac
 
 // n_pairs independent problems, descriptors in device memory (batched solver / benchmark path)
 template <int MODE, int NP, bool AFF>
-__global__ void __launch_bounds__(SPB_THREADS, Occ<MODE>::CTAS)
+__global__ void __launch_bounds__(SPB_THREADS, Occ<MODE, NP>::CTAS)
 k_align_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs, float irls_eps,
                float* __restrict__ work, int64_t work_stride) {
     constexpr int NACC = Sizes<MODE, NP>::NACC;
@@ -719,7 +731,7 @@ static inline int ctas_for(int n_tiles, int n_pairs) {
     // every warp streams a strided set of tiles through its own ring; aim at ~4 waves of 3 CTAs/SM over
     // all pairs so the tail wave is small, but keep >= 2 tiles per warp when there is enough work
     const int max_ctas = (n_tiles + SPB_WARPS - 1) / SPB_WARPS;
-    int want = (148 * 3 * 4 + n_pairs - 1) / (n_pairs > 0 ? n_pairs : 1);
+    int want = (148 * 4 * 4 + n_pairs - 1) / (n_pairs > 0 ? n_pairs : 1);
     if (want > max_ctas) want = max_ctas;
     if (want < 1) want = 1;
     return want;

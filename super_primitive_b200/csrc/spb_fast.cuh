@@ -18,24 +18,30 @@
 #include "spb_common.cuh"
 
 #ifndef SPB_PIPE
-#define SPB_PIPE 2                             // points per lane whose taps are in flight (1 or 2)
+#define SPB_PIPE 1                             // points per lane whose taps are in flight (1 or 2)
 #endif
 #ifndef SPB_WSTAGES
-#define SPB_WSTAGES 3                          // ring slots per warp
+#define SPB_WSTAGES 2                          // ring slots per warp
 #endif
 #define SPB_SLOT_WORDS (5 * SPB_TILE + 4)      // 5 arrays of 128 words + header {seg, cnt, unpadded start, -}
-#define SPB_NSHIFT 2048                        // segments whose shift is cached in shared memory
+#define SPB_NSHIFT 512                         // segments whose shift is cached in shared memory
 #define SPB_FAST_DYN_SMEM (SPB_WARPS * SPB_WSTAGES * SPB_SLOT_WORDS * 4 + SPB_WARPS * SPB_WSTAGES * 8)
 
+// context words, grouped so the hot loop reads them as eight 16-byte vectors (LDS.128):
+//   V0..V2 = rows of [M | t] with M = R diag(1/fx, 1/fy, 1);  V3 = (ax, bx, ay, by);  V4 = (sx, sy, tau, ea);
+//   V5 = (bb, -, cu, cv);  V6 = (cu^2, cu cv, cu cv, cv^2);  V7 = (cx, cy, -, -)
 enum FastSlot {
-    F_M = 0,                       // 9: R diag(1/fx, 1/fy, 1) row-major
-    F_T = 9,                       // 3
     F_AX = 12, F_BX, F_AY, F_BY,   // xn = ax x_ + bx
     F_SX = 16, F_SY, F_TAU, F_EA,
-    F_BB = 20, F_CU, F_CV, F_CUU,  // cu, cv, cu^2
-    F_CUV = 24, F_CVV, F_CX, F_CY,
-    F_N = 28
+    F_BB = 20, F_PAD0,
+    F_CU = 22, F_CV,
+    F_CUU = 24, F_CUV,
+    F_CUV2 = 26, F_CVV,
+    F_CX = 28, F_CY,
+    F_N = 32
 };
+#define F_MAT(i, j) (4 * (i) + (j))
+#define F_TR(i) (4 * (i) + 3)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -71,13 +77,15 @@ __device__ __forceinline__ void fill_fast_ctx(float* s, const SpbPair& pr, const
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const float r0 = pr.pose[4 * i], r1 = pr.pose[4 * i + 1], r2 = pr.pose[4 * i + 2];
-            s[F_M + 3 * i + 0] = r0 * ifx;
-            s[F_M + 3 * i + 1] = r1 * ify;
-            s[F_M + 3 * i + 2] = r2;
-            s[F_T + i] = pr.pose[4 * i + 3];
+            s[F_MAT(i, 0)] = r0 * ifx;
+            s[F_MAT(i, 1)] = r1 * ify;
+            s[F_MAT(i, 2)] = r2;
+            s[F_TR(i)] = pr.pose[4 * i + 3];
         }
         s[F_CX] = cx;
         s[F_CY] = cy;
+        s[F_CY + 1] = 0.f;
+        s[F_CY + 2] = 0.f;
     } else if (threadIdx.x == 1) {
         const float tiw = 2.0f * (1.0f / (float)(W - 1)), tih = 2.0f * (1.0f / (float)(H - 1));
         const float sx = 0.5f * (float)(pr.Wl - 1), sy = 0.5f * (float)(pr.Hl - 1);
@@ -92,7 +100,8 @@ __device__ __forceinline__ void fill_fast_ctx(float* s, const SpbPair& pr, const
         s[F_AY] = fyt * tih; s[F_BY] = fmaf(cyt, tih, -1.0f);
         s[F_SX] = sx; s[F_SY] = sy; s[F_TAU] = pr.tau; s[F_EA] = ea; s[F_BB] = b;
         const float cu = -ea * (sx * tiw) * fxt, cv = -ea * (sy * tih) * fyt;
-        s[F_CU] = cu; s[F_CV] = cv; s[F_CUU] = cu * cu; s[F_CUV] = cu * cv; s[F_CVV] = cv * cv;
+        s[F_CU] = cu; s[F_CV] = cv; s[F_CUU] = cu * cu; s[F_CUV] = cu * cv; s[F_CUV2] = cu * cv; s[F_CVV] = cv * cv;
+        s[F_PAD0] = 0.f;
     }
 }
 
@@ -106,27 +115,30 @@ struct Proj {
 
 __device__ __forceinline__ bool project_point(const float* __restrict__ c, uint32_t w, float logd, float shift, int Wl,
                                               Proj& q) {
-    const float u = (float)(w & 0xffffu) - c[F_CX];
-    const float v = (float)((w >> 16) & 0x7fffu) - c[F_CY];
+    const float4* c4 = reinterpret_cast<const float4*>(c);
+    const float4 r0 = c4[0], r1 = c4[1], r2 = c4[2], pa = c4[3], pb = c4[4];
+    const float2 cc = *reinterpret_cast<const float2*>(c + F_CX);
+    const float u = (float)(w & 0xffffu) - cc.x;
+    const float v = (float)((w >> 16) & 0x7fffu) - cc.y;
     const float z = __expf(logd + shift);
     q.uc = u;
     q.vc = v;
-    const float qx = fmaf(c[F_M + 0], u, fmaf(c[F_M + 1], v, c[F_M + 2]));
-    const float qy = fmaf(c[F_M + 3], u, fmaf(c[F_M + 4], v, c[F_M + 5]));
-    const float qz = fmaf(c[F_M + 6], u, fmaf(c[F_M + 7], v, c[F_M + 8]));
+    const float qx = fmaf(r0.x, u, fmaf(r0.y, v, r0.z));
+    const float qy = fmaf(r1.x, u, fmaf(r1.y, v, r1.z));
+    const float qz = fmaf(r2.x, u, fmaf(r2.y, v, r2.z));
     q.zs = z;
-    q.Yx = fmaf(z, qx, c[F_T + 0]);
-    q.Yy = fmaf(z, qy, c[F_T + 1]);
-    q.Yz = fmaf(z, qz, c[F_T + 2]);
+    q.Yx = fmaf(z, qx, r0.w);
+    q.Yy = fmaf(z, qy, r1.w);
+    q.Yz = fmaf(z, qz, r2.w);
     q.live = fabsf(q.Yz) > 1e-6f;                                  // guarded reciprocal, core/ops.py:22,33-34
     q.rho = q.live ? __fdividef(1.0f, q.Yz) : 1e-6f;
     q.xb = q.Yx * q.rho;
     q.yb = q.Yy * q.rho;
-    const float xn = fmaf(q.xb, c[F_AX], c[F_BX]);
-    const float yn = fmaf(q.yb, c[F_AY], c[F_BY]);
-    const bool ok = (w >> 31) && (z > 1e-7f) && (fabsf(xn) <= 0.99f) && (fabsf(yn) <= 0.99f) && (q.Yz > c[F_TAU]);
-    const float ix = fmaf(xn, c[F_SX], c[F_SX]);
-    const float iy = fmaf(yn, c[F_SY], c[F_SY]);
+    const float xn = fmaf(q.xb, pa.x, pa.y);
+    const float yn = fmaf(q.yb, pa.z, pa.w);
+    const bool ok = (w >> 31) && (z > 1e-7f) && (fabsf(xn) <= 0.99f) && (fabsf(yn) <= 0.99f) && (q.Yz > pb.z);
+    const float ix = fmaf(xn, pb.x, pb.x);
+    const float iy = fmaf(yn, pb.y, pb.y);
     const float fxf = floorf(ix), fyf = floorf(iy);
     q.fx = ix - fxf;
     q.fy = iy - fyf;
@@ -178,7 +190,7 @@ __device__ __forceinline__ void point_grad(const float* __restrict__ c, const Ta
     if (AFF) { acc[13] = fmaf(c[F_EA], ga, acc[13]); acc[14] -= gb; }
     acc[15] += 1.0f;
     // d cost / d k_b = gY . (R X) = gY . Y - gY . t, and gY . Y == 0 when the reciprocal is live
-    gk -= fmaf(gYx, c[F_T + 0], fmaf(gYy, c[F_T + 1], gYz * c[F_T + 2]));
+    gk -= fmaf(gYx, c[F_TR(0)], fmaf(gYy, c[F_TR(1)], gYz * c[F_TR(2)]));
     if (!q.live) gk += fmaf(gYx, q.Yx, gYy * q.Yy);
 }
 
@@ -228,13 +240,13 @@ __device__ __forceinline__ void point_gn(const float* __restrict__ c, const Taps
         const float xy = xb * yb;
         mu2 = -rho * xb; mu3 = -xy;                 mu4 = fmaf(xb, xb, 1.0f); mu5 = -yb;
         mv2 = -rho * yb; mv3 = -fmaf(yb, yb, 1.0f); mv4 = xy;                 mv5 = xb;
-        mu6 = rho * fmaf(xb, c[F_T + 2], -c[F_T + 0]);
-        mv6 = rho * fmaf(yb, c[F_T + 2], -c[F_T + 1]);
+        mu6 = rho * fmaf(xb, c[F_TR(2)], -c[F_TR(0)]);
+        mv6 = rho * fmaf(yb, c[F_TR(2)], -c[F_TR(1)]);
     } else {                                         // constant reciprocal: no z-derivative (never taken in practice)
         mu2 = 0.f; mu3 = 0.f; mu4 = rho * q.Yz; mu5 = -rho * q.Yy;
         mv2 = 0.f; mv3 = -rho * q.Yz; mv4 = 0.f; mv5 = rho * q.Yx;
-        mu6 = rho * (q.Yx - c[F_T + 0]);
-        mv6 = rho * (q.Yy - c[F_T + 1]);
+        mu6 = rho * (q.Yx - c[F_TR(0)]);
+        mv6 = rho * (q.Yy - c[F_TR(1)]);
     }
     // pu = Guu mu + Guv mv ; pv = Guv mu + Gvv mv   (index 0: mv0 = 0, index 1: mu1 = 0)
     const float pu0 = Guu * rho;

@@ -1,0 +1,150 @@
+// Packed-FP32 (FFMA2 / FMUL2, sm_100) formulation of the 6-column Gauss-Newton accumulation.
+//
+// Blackwell issues two independent FP32 FMAs per FFMA2 instruction and accepts a scalar register as a
+// broadcast operand (SASS `R.F32`), so every rank-1 update `acc[r][c..c+1] += m_r * p[c..c+1]` of the
+// arrowhead blocks is ONE instruction instead of two.  The kernel is issue-bound, not FMA-pipe-bound,
+// so halving the instruction count of the accumulation is a direct win.  Same arithmetic as point_gn
+// (spb_fast.cuh) up to the association order inside each two-term sum.
+#pragma once
+#include "spb_fast.cuh"
+
+struct GnAcc6 {            // upper triangle of the 6x6 pose block, g_p, cost terms (canonical order in store())
+    float2 a00, a02, a04;  // (0,0)(0,1) (0,2)(0,3) (0,4)(0,5)
+    float a11;
+    float2 a12, a14;       // (1,2)(1,3) (1,4)(1,5)
+    float2 a22, a24;       // (2,2)(2,3) (2,4)(2,5)
+    float a33;
+    float2 a34;            // (3,4)(3,5)
+    float2 a44;            // (4,4)(4,5)
+    float a55;
+    float2 g01, g23, g45;
+    float cost, wcost, nv;
+    __device__ __forceinline__ void zero() {
+        const float2 z = make_float2(0.f, 0.f);
+        a00 = a02 = a04 = a12 = a14 = a22 = a24 = a34 = a44 = g01 = g23 = g45 = z;
+        a11 = a33 = a55 = cost = wcost = nv = 0.f;
+    }
+    __device__ __forceinline__ void store(float (&o)[30]) const {
+        o[0] = a00.x; o[1] = a00.y; o[2] = a02.x; o[3] = a02.y; o[4] = a04.x; o[5] = a04.y;
+        o[6] = a11; o[7] = a12.x; o[8] = a12.y; o[9] = a14.x; o[10] = a14.y;
+        o[11] = a22.x; o[12] = a22.y; o[13] = a24.x; o[14] = a24.y;
+        o[15] = a33; o[16] = a34.x; o[17] = a34.y;
+        o[18] = a44.x; o[19] = a44.y; o[20] = a55;
+        o[21] = g01.x; o[22] = g01.y; o[23] = g23.x; o[24] = g23.y; o[25] = g45.x; o[26] = g45.y;
+        o[27] = cost; o[28] = wcost; o[29] = nv;
+    }
+};
+
+struct GnSeg6 {            // depth column of the tile's segment: B[0..5], D, g_d
+    float2 b01, b23, b45;
+    float d, gd;
+    __device__ __forceinline__ void zero() {
+        b01 = b23 = b45 = make_float2(0.f, 0.f);
+        d = gd = 0.f;
+    }
+    __device__ __forceinline__ void store(float (&o)[8]) const {
+        o[0] = b01.x; o[1] = b01.y; o[2] = b23.x; o[3] = b23.y; o[4] = b45.x; o[5] = b45.y; o[6] = d; o[7] = gd;
+    }
+};
+
+// scalar * pair (+ pair): the scalar is a broadcast operand, no extra instruction
+__device__ __forceinline__ float2 fma2(float s, float2 b, float2 c) { return __ffma2_rn(make_float2(s, s), b, c); }
+__device__ __forceinline__ float2 mul2(float s, float2 b) { return __fmul2_rn(make_float2(s, s), b); }
+
+// value and slope pair (dI/dix, dI/diy) of one channel
+__device__ __forceinline__ void blend2(float nw, float ne, float sw, float se, float fx, float fy, float& val,
+                                       float2& d) {
+    const float d0 = ne - nw;
+    const float d1 = se - sw;
+    const float top = fmaf(fx, d0, nw);
+    const float bot = fmaf(fx, d1, sw);
+    d.y = bot - top;
+    val = fmaf(fy, d.y, top);
+    d.x = fmaf(fy, d1 - d0, d0);
+}
+
+__device__ __forceinline__ void point_gn6_packed(const float* __restrict__ c, const Taps4& tp, const Proj& q,
+                                                 float Is0, float Is1, float Is2, float irls_eps, GnAcc6& A,
+                                                 GnSeg6& S) {
+    float I[3];
+    float2 d[3];
+    blend2(tp.nw.x, tp.ne.x, tp.sw.x, tp.se.x, q.fx, q.fy, I[0], d[0]);
+    blend2(tp.nw.y, tp.ne.y, tp.sw.y, tp.se.y, q.fx, q.fy, I[1], d[1]);
+    blend2(tp.nw.z, tp.ne.z, tp.sw.z, tp.se.z, q.fx, q.fy, I[2], d[2]);
+    const float Is[3] = {Is0, Is1, Is2};
+    const float ea = c[F_EA], bb = c[F_BB];
+    // GA = (Guu, Guv), GB = (Guv, Gvv), H = (hu, hv): image-gradient moments over the channels
+    float2 GA = make_float2(0.f, 0.f), GB = GA, H = GA;
+    float cost = 0.f, wcost = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float r = Is[ch] - fmaf(ea, I[ch], bb);
+        const float ar = fabsf(r);
+        const float wgt = __fdividef(1.0f, fmaxf(ar, irls_eps));     // IRLS weight of the L1 objective
+        const float wr = wgt * r;
+        cost += ar;
+        wcost = fmaf(wr, r, wcost);
+        const float2 wd = mul2(wgt, d[ch]);                          // (w dIx, w dIy)
+        GA = fma2(wd.x, d[ch], GA);
+        GB = fma2(wd.y, d[ch], GB);
+        H = fma2(wr, d[ch], H);
+    }
+    GA = __fmul2_rn(GA, *reinterpret_cast<const float2*>(c + F_CUU));     // (cu^2, cu cv)
+    GB = __fmul2_rn(GB, *reinterpret_cast<const float2*>(c + F_CUV2));    // (cu cv, cv^2)
+    H = __fmul2_rn(H, *reinterpret_cast<const float2*>(c + F_CU));        // (cu, cv)
+    const float Guu = GA.x, Guv = GA.y, Gvv = GB.y, hu = H.x, hv = H.y;
+
+    // mu = d x_/d(xi,k), mv = d y_/d(xi,k) with mu0 = rho, mu1 = 0, mv0 = 0, mv1 = rho
+    const float rho = q.rho, xb = q.xb, yb = q.yb;
+    float2 mu23, mu45, mv23, mv45;
+    float mu6, mv6;
+    if (q.live) {
+        const float xy = xb * yb;
+        mu23 = make_float2(-rho * xb, -xy);
+        mu45 = make_float2(fmaf(xb, xb, 1.0f), -yb);
+        mv23 = make_float2(-rho * yb, -fmaf(yb, yb, 1.0f));
+        mv45 = make_float2(xy, xb);
+        mu6 = rho * fmaf(xb, c[F_TR(2)], -c[F_TR(0)]);
+        mv6 = rho * fmaf(yb, c[F_TR(2)], -c[F_TR(1)]);
+    } else {                                         // constant reciprocal: no z-derivative (never taken in practice)
+        mu23 = make_float2(0.f, 0.f);
+        mu45 = make_float2(rho * q.Yz, -rho * q.Yy);
+        mv23 = make_float2(0.f, -rho * q.Yz);
+        mv45 = make_float2(0.f, rho * q.Yx);
+        mu6 = rho * (q.Yx - c[F_TR(0)]);
+        mv6 = rho * (q.Yy - c[F_TR(1)]);
+    }
+    // pu = Guu mu + Guv mv ; pv = Guv mu + Gvv mv
+    const float2 pu01 = mul2(rho, GA);                               // (Guu rho, Guv rho)
+    const float pv1 = Gvv * rho;
+    const float2 pu23 = fma2(Guu, mu23, mul2(Guv, mv23)), pv23 = fma2(Guv, mu23, mul2(Gvv, mv23));
+    const float2 pu45 = fma2(Guu, mu45, mul2(Guv, mv45)), pv45 = fma2(Guv, mu45, mul2(Gvv, mv45));
+    const float2 p6 = fma2(mu6, GA, mul2(mv6, GB));                  // (pu6, pv6)
+
+    // pose block, upper triangle
+    A.a00 = fma2(rho, pu01, A.a00);
+    A.a02 = fma2(rho, pu23, A.a02);
+    A.a04 = fma2(rho, pu45, A.a04);
+    A.a11 = fmaf(rho, pv1, A.a11);
+    A.a12 = fma2(rho, pv23, A.a12);
+    A.a14 = fma2(rho, pv45, A.a14);
+    A.a22 = fma2(mu23.x, pu23, fma2(mv23.x, pv23, A.a22));
+    A.a24 = fma2(mu23.x, pu45, fma2(mv23.x, pv45, A.a24));
+    A.a33 = fmaf(mu23.y, pu23.y, fmaf(mv23.y, pv23.y, A.a33));
+    A.a34 = fma2(mu23.y, pu45, fma2(mv23.y, pv45, A.a34));
+    A.a44 = fma2(mu45.x, pu45, fma2(mv45.x, pv45, A.a44));
+    A.a55 = fmaf(mu45.y, pu45.y, fmaf(mv45.y, pv45.y, A.a55));
+    // g_p = J^T W r
+    A.g01 = fma2(rho, H, A.g01);
+    A.g23 = fma2(hu, mu23, fma2(hv, mv23, A.g23));
+    A.g45 = fma2(hu, mu45, fma2(hv, mv45, A.g45));
+    A.cost += cost;
+    A.wcost += wcost;
+    A.nv += 1.0f;
+    // depth column of this tile's segment
+    S.b01 = fma2(rho, p6, S.b01);
+    S.b23 = fma2(p6.x, mu23, fma2(p6.y, mv23, S.b23));
+    S.b45 = fma2(p6.x, mu45, fma2(p6.y, mv45, S.b45));
+    S.d = fmaf(mu6, p6.x, fmaf(mv6, p6.y, S.d));
+    S.gd = fmaf(mu6, hu, fmaf(mv6, hv, S.gd));
+}
