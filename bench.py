@@ -119,28 +119,28 @@ def build_batch(pairs, device, seed0=0, level=0):
         noise = (torch.rand(trg.image.shape, generator=g) * 0.02 - 0.01).to(device)
         timg = (trg.image + noise).contiguous()
         simg = (src.image + noise.flip(-1)).contiguous()
-        src_rgb = geom.source_samples(simg).clone()
+        src_rgb, pack = geom.level_buffers(simg)
         trg_rgba = pack_rgba(timg)[0].clone()
         dk = (torch.rand(N, generator=g) * 0.1 - 0.05)
         pose = pose0.clone()
         pose[:3, 3] += (torch.rand(3, generator=g) - 0.5) * 0.01
-        problems.append(dict(geom=geom, src_rgb=src_rgb, trg_rgba=trg_rgba, K_trg=trg.K, pose=pose.to(device),
+        problems.append(dict(geom=geom, src_rgb=src_rgb, pack=pack, trg_rgba=trg_rgba, K_trg=trg.K, pose=pose.to(device),
                              k=(k0 + dk).to(device)))
     batch = AlignmentBatch(problems, with_affine=False, irls_eps=1e-3)
     return batch, problems
 
 
 class HostStaged:
-    """End-to-end arm: every step re-uploads the step's inputs (compact geometry, cached source samples,
-    target image, pose, log-depth seeds) from pinned host memory, runs the iteration, and reads the
-    updated poses / seeds / cost back to the host."""
+    """End-to-end arm: every step re-uploads the step's inputs (the tile-major level buffer = compact geometry +
+    cached source samples, the target image, pose, log-depth seeds) from pinned host memory, runs the
+    iteration, and reads the updated poses / seeds / cost back to the host."""
 
     def __init__(self, batch, problems):
         self.batch = batch
         self.dev_bufs, self.host_bufs = [], []
         seen = set()
         for p in problems:
-            for t in (p['geom'].uv, p['geom'].logd, p['src_rgb'], p['trg_rgba']):
+            for t in (p['pack'], p['trg_rgba']):
                 if id(t) in seen:
                     continue
                 seen.add(id(t))
@@ -381,7 +381,7 @@ def main():
                                       "forward + backward + Adam.step) on ONE 640x480 / 64-segment pair, finest "
                                       f"level, float32, {cores} torch threads (fastest candidate on {host_cores()} host "
                                       f"cores); {ms:.1f} ms/iter"}
-        ws = batch.points_total * 20 + sum(p['trg_rgba'].numel() * 4 for p in problems)
+        ws = sum(p['pack'].numel() * 4 + p['trg_rgba'].numel() * 4 for p in problems)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
                 "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

@@ -30,6 +30,7 @@ extern "C" {
 #define SPB_ELIMIT (-2)
 
 #define SPB_TILE 128          /* points per warp-tile (one segment per tile)            */
+#define SPB_PACK_WORDS (4 + 5 * SPB_TILE)   /* words per tile block: {seg,cnt,ustart,0} + 5 arrays */
 #define SPB_PAD 4             /* every segment's point range is padded to this multiple  */
 #define SPB_PAIR_NOUT 16      /* floats per pair, gradient mode (layout below)           */
 #define SPB_GN_NPOSE 8        /* pose-block columns: 6 twist + 2 target affine           */
@@ -57,7 +58,9 @@ typedef struct SpbGeom {
 /* ---- one (source geometry, target image) pair ------------------------------------------------ */
 typedef struct SpbPair {
     const float* trg_rgba;     /* [Hl][Wl][4] target level image, RGBA-interleaved float32            */
-    const float* src_rgb;      /* [3][n_pad] cached source samples at this level (planar)             */
+    const float* src_rgb;      /* [3][n_pad] cached source samples at this level (planar; statistics path) */
+    const uint32_t* tile_pack; /* [n_tiles][SPB_PACK_WORDS] tile-major copy of {header, uv, logd, r, g, b}:
+                                  what the fused kernel streams, one bulk copy per tile (spb_build_tile_pack) */
     const float* K_trg;        /* [9] target intrinsics (geometry-level K of the target frame)        */
     const float* pose;         /* [16] row-major 4x4 (source -> target)                               */
     const float* k;            /* [n_seg] log-depth seeds of the source segments                      */
@@ -110,6 +113,11 @@ int spb_pack_rgba(const float* planar, int64_t img_stride, int n_img, int Hl, in
  * pixel scaled to the level (core/dense_optim.py:315-317 / :190-192). out = [3][n_pad]. */
 int spb_sample_source(const SpbGeom* geom, const float* src_planar, int Hl, int Wl, float* out,
                       void* stream);
+
+/* Tile-major level buffer streamed by the fused kernel: for every tile one contiguous block of
+ * SPB_PACK_WORDS 32-bit words = header {segment, count, unpadded start, 0} + uv[128] + logd[128] + r[128] +
+ * g[128] + b[128] (zero-filled beyond count).  src_rgb = output of spb_sample_source for the level. */
+int spb_build_tile_pack(const SpbGeom* geom, const float* src_rgb, uint32_t* pack, void* stream);
 
 /* ================================ per-iteration hot path ====================================== */
 

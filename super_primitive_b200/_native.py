@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("SPB200_LIB") or os.path.join(_HERE, "csrc", "libspb20
 
 TILE = 128
 PAD = 4
+PACK_WORDS = 4 + 5 * TILE
 PAIR_NOUT = 16
 GN_PAIR_NOUT = 48
 GN_SEG_NOUT = 10
@@ -34,7 +35,8 @@ class SpbGeom(C.Structure):
 
 
 class SpbPair(C.Structure):
-    _fields_ = [("trg_rgba", C.c_void_p), ("src_rgb", C.c_void_p), ("K_trg", C.c_void_p),
+    _fields_ = [("trg_rgba", C.c_void_p), ("src_rgb", C.c_void_p), ("tile_pack", C.c_void_p),
+                ("K_trg", C.c_void_p),
                 ("pose", C.c_void_p), ("k", C.c_void_p), ("aff_src", C.c_void_p),
                 ("aff_trg", C.c_void_p), ("geom", C.c_int32), ("Hl", C.c_int32),
                 ("Wl", C.c_int32), ("tau", C.c_float)]
@@ -53,6 +55,7 @@ _PROTOS = {
     "spb_compact_fill": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spb_pack_rgba": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
     "spb_sample_source": (_i, [C.POINTER(SpbGeom), _vp, _i, _i, _vp, _vp]),
+    "spb_build_tile_pack": (_i, [C.POINTER(SpbGeom), _vp, _vp, _vp]),
     "spb_cost_grad": (_i, [C.POINTER(SpbGeom), C.POINTER(SpbPair), _i, _vp, _vp, _vp,
                            C.POINTER(SpbStats), _vp]),
     "spb_cost_grad_points": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SpbPair), _vp, _vp, _vp]),

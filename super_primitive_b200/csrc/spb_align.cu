@@ -360,6 +360,12 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
 #include "spb_fast.cuh"
 #include "spb_gn_packed.cuh"
 
+#ifndef SPB_UNROLL
+#define SPB_UNROLL 1                           // unroll factor of the per-lane point loop
+#endif
+#define SPB_DO_PRAGMA(x) _Pragma(#x)
+#define SPB_PRAGMA_UNROLL(n) SPB_DO_PRAGMA(unroll n)
+
 // ------------------------------------------------------------------------------------------------
 // Hot-path body: per-warp bulk-async pipelines (see spb_fast.cuh).  grid = (ctas_per_pair, pairs)
 //   part_pair : [cta][NACC]      part_seg : [tile][NSEG]
@@ -376,7 +382,6 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* ring = s_dyn + warp * (SPB_WSTAGES * SPB_SLOT_WORDS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + SPB_WARPS * SPB_WSTAGES * SPB_SLOT_WORDS) + warp * SPB_WSTAGES;
-    const int4* tiles = reinterpret_cast<const int4*>(g.tiles);
 
     if (threadIdx.x < 32) fill_fast_ctx(s_ctx, pr, g.K, g.H, g.W);
     if (lane == 0) {
@@ -391,31 +396,20 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
 
     const int WS = gridDim.x * SPB_WARPS;                  // tile stride of this warp
     const int t_first = blockIdx.x * SPB_WARPS + warp;
-    const size_t plane = (size_t)g.n_pad;
+    const uint32_t* pack = pr.tile_pack;
 
-    auto issue = [&](const int4 td, int slot) {            // lane 0: descriptor + 5 bulk copies -> ring slot
-        uint32_t* sl = ring + slot * SPB_SLOT_WORDS;
-        sl[0] = (uint32_t)td.x; sl[1] = (uint32_t)td.z; sl[2] = (uint32_t)td.w;
-        const uint32_t bytes = (uint32_t)((td.z + 3) & ~3) * 4u;
+    // producer (lane 0): ONE bulk copy brings the whole tile block (header + uv + logd + r + g + b)
+    auto issue = [&](int t, int slot) {
         const uint32_t bar = smem_u32(bars + slot);
-        const uint32_t dst = smem_u32(sl + 4);
-        mbar_expect_tx(bar, 5u * bytes);
-        bulk_g2s(dst, g.uv + td.y, bytes, bar);
-        bulk_g2s(dst + SPB_TILE * 4, g.logd + td.y, bytes, bar);
-        bulk_g2s(dst + 2 * SPB_TILE * 4, pr.src_rgb + td.y, bytes, bar);
-        bulk_g2s(dst + 3 * SPB_TILE * 4, pr.src_rgb + plane + td.y, bytes, bar);
-        bulk_g2s(dst + 4 * SPB_TILE * 4, pr.src_rgb + 2 * plane + td.y, bytes, bar);
+        mbar_expect_tx(bar, SPB_PACK_WORDS * 4u);
+        bulk_g2s(smem_u32(ring + slot * SPB_SLOT_WORDS), pack + (size_t)t * SPB_PACK_WORDS, SPB_PACK_WORDS * 4u, bar);
     };
-
-    int4 td_pref = make_int4(0, 0, 0, 0);
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < SPB_WSTAGES - 1; ++s) {
             const int t = t_first + s * WS;
-            if (t < g.n_tiles) issue(__ldg(tiles + t), s);
+            if (t < g.n_tiles) issue(t, s);
         }
-        const int tp = t_first + (SPB_WSTAGES - 1) * WS;
-        if (tp < g.n_tiles) td_pref = __ldg(tiles + tp);
     }
 
     const float4* trg = reinterpret_cast<const float4*>(pr.trg_rgba);
@@ -432,11 +426,8 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     for (int t = t_first; t < g.n_tiles; t += WS) {
         if (lane == 0) {
             const int tn = t + (SPB_WSTAGES - 1) * WS;
-            if (tn < g.n_tiles) issue(td_pref, fill);
-            const int tp = tn + WS;
-            if (tp < g.n_tiles) td_pref = __ldg(tiles + tp);
+            if (tn < g.n_tiles) issue(tn, fill);
         }
-        __syncwarp();
         mbar_wait(smem_u32(bars + slot), phase);
         const uint32_t* sl = ring + slot * SPB_SLOT_WORDS;
         const int sidx = (int)sl[0], cnt = (int)sl[1];
@@ -448,8 +439,15 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
         for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
         GnSeg6 pseg;
         pseg.zero();
-        auto consume = [&](const Proj& q, const Taps4& tp, bool ok, int i) {
-            if (ok) {
+        // padding entries of a partial tile are zero words: uv bit 31 clear => invalid, no bounds test needed
+        (void)cnt;
+        SPB_PRAGMA_UNROLL(SPB_UNROLL)
+        for (int j = 0; j < SPB_PPT; ++j) {
+            const int i = j * 32 + lane;
+            Proj q;
+            if (project_point(c, s_uv[i], s_f[SPB_TILE + i], shift, Wl, q)) {
+                Taps4 tp;
+                load_taps(trg, Wl, q.off, tp);
                 const float i0 = s_f[2 * SPB_TILE + i], i1 = s_f[3 * SPB_TILE + i], i2 = s_f[4 * SPB_TILE + i];
                 if constexpr (MODE == MODE_GRAD)
                     point_grad<AFF>(c, tp, q, i0, i1, i2, acc, seg[0]);
@@ -458,46 +456,7 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
                 else
                     point_gn<NP, NACC, NSEG>(c, tp, q, i0, i1, i2, irls_eps, acc, seg);
             }
-        };
-#if SPB_PIPE == 2
-        // software pipeline: the taps of point j+1 are requested before point j is consumed, so every
-        // lane keeps two gathers in flight (the target image is the only operand not staged by TMA)
-        Proj qa, qb;
-        Taps4 ta, tb;
-        bool oka = false, okb = false;
-        if (lane < cnt) {
-            oka = project_point(c, s_uv[lane], s_f[SPB_TILE + lane], shift, Wl, qa);
-            load_taps(trg, Wl, qa.off, ta);
         }
-#pragma unroll
-        for (int j = 0; j < SPB_PPT; j += 2) {
-            const int i0 = j * 32 + lane, i1 = i0 + 32, i2 = i0 + 64;
-            okb = false;
-            if (i1 < cnt) {
-                okb = project_point(c, s_uv[i1], s_f[SPB_TILE + i1], shift, Wl, qb);
-                load_taps(trg, Wl, qb.off, tb);
-            }
-            consume(qa, ta, oka, i0);
-            oka = false;
-            if (j + 2 < SPB_PPT && i2 < cnt) {
-                oka = project_point(c, s_uv[i2], s_f[SPB_TILE + i2], shift, Wl, qa);
-                load_taps(trg, Wl, qa.off, ta);
-            }
-            consume(qb, tb, okb, i1);
-        }
-#else
-#pragma unroll
-        for (int j = 0; j < SPB_PPT; ++j) {
-            const int i = j * 32 + lane;
-            if (i < cnt) {
-                Proj q;
-                Taps4 tp;
-                const bool ok = project_point(c, s_uv[i], s_f[SPB_TILE + i], shift, Wl, q);
-                if (ok) load_taps(trg, Wl, q.off, tp);
-                consume(q, tp, ok, i);
-            }
-        }
-#endif
         if constexpr (PACKED) pseg.store(seg);
         tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
         __syncwarp();                                      // every lane is done with this slot

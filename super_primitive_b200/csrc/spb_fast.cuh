@@ -1,11 +1,12 @@
 // Hot-path body of the fused alignment kernel (sm_100a): per-warp bulk-async pipelines + lean math.
 //
-// Streaming operands (uv, logd, cached source rgb) of a tile travel global -> shared memory with
-// cp.async.bulk (TMA 1-D) into a private ring of SPB_WSTAGES slots PER WARP, completing on an
-// mbarrier; lane 0 of the warp issues the copies SPB_WSTAGES-1 tiles ahead.  There is no CTA-wide
-// barrier in the loop, tile descriptors ride in the slot header and the per-segment depth shifts
-// live in shared memory, so nothing on a tile's critical path waits on global memory except the
-// four bilinear taps of the target image.
+// Streaming operands (uv, logd, cached source rgb) of a tile are stored tile-major in HBM
+// (SpbPair.tile_pack: header + five 128-word arrays = one contiguous 2576-byte block per tile) and travel
+// global -> shared memory with ONE cp.async.bulk (TMA 1-D) per tile into a private ring of SPB_WSTAGES
+// slots PER WARP, completing on an mbarrier; one elected lane issues the copy SPB_WSTAGES-1 tiles ahead.
+// There is no CTA-wide barrier in the loop, the tile descriptor is the block header and the per-segment
+// depth shifts live in shared memory, so nothing on a tile's critical path waits on global memory except
+// the four bilinear taps of the target image.
 //
 // Math (same quantities as eval_point in spb_align.cu, reorganised to cut instructions):
 //   Y = z (M u~) + t with M = R diag(1/fx, 1/fy, 1), u~ = (u - cx, v - cy, 1)   [folds unproject + rotate]
@@ -23,7 +24,7 @@
 #ifndef SPB_WSTAGES
 #define SPB_WSTAGES 2                          // ring slots per warp
 #endif
-#define SPB_SLOT_WORDS (5 * SPB_TILE + 4)      // 5 arrays of 128 words + header {seg, cnt, unpadded start, -}
+#define SPB_SLOT_WORDS SPB_PACK_WORDS           // one tile block: header {seg, cnt, unpadded start, -} + 5 arrays
 #define SPB_NSHIFT 512                         // segments whose shift is cached in shared memory
 #define SPB_FAST_DYN_SMEM (SPB_WARPS * SPB_WSTAGES * SPB_SLOT_WORDS * 4 + SPB_WARPS * SPB_WSTAGES * 8)
 
@@ -142,7 +143,7 @@ __device__ __forceinline__ bool project_point(const float* __restrict__ c, uint3
     const float fxf = floorf(ix), fyf = floorf(iy);
     q.fx = ix - fxf;
     q.fy = iy - fyf;
-    q.off = ok ? ((int)fyf * Wl + (int)fxf) : 0;                   // invalid points load texel 0 (never used)
+    q.off = (int)fyf * Wl + (int)fxf;
     return ok;
 }
 

@@ -206,6 +206,35 @@ extern "C" int spb_sample_source(const SpbGeom* geom, const float* src_planar, i
     return SPB_OK;
 }
 
+// tile-major level buffer: one warp per tile copies header + the five 128-word arrays (coalesced)
+__global__ void k_build_tile_pack(const __grid_constant__ SpbGeom g, const float* __restrict__ rgb,
+                                  uint32_t* __restrict__ pack) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= g.n_tiles) return;
+    const int4 td = reinterpret_cast<const int4*>(g.tiles)[t];
+    uint32_t* o = pack + (size_t)t * SPB_PACK_WORDS;
+    if (lane < 4) o[lane] = lane == 0 ? (uint32_t)td.x : (lane == 1 ? (uint32_t)td.z : (lane == 2 ? (uint32_t)td.w : 0u));
+    const uint32_t* rgbu = reinterpret_cast<const uint32_t*>(rgb);
+    const uint32_t* lu = reinterpret_cast<const uint32_t*>(g.logd);
+    for (int i = lane; i < SPB_TILE; i += 32) {
+        const bool on = i < td.z;
+        const size_t p = (size_t)td.y + (on ? i : 0);
+        o[4 + i] = on ? g.uv[p] : 0u;
+        o[4 + SPB_TILE + i] = on ? lu[p] : 0u;
+        o[4 + 2 * SPB_TILE + i] = on ? rgbu[p] : 0u;
+        o[4 + 3 * SPB_TILE + i] = on ? rgbu[(size_t)g.n_pad + p] : 0u;
+        o[4 + 4 * SPB_TILE + i] = on ? rgbu[2 * (size_t)g.n_pad + p] : 0u;
+    }
+}
+
+extern "C" int spb_build_tile_pack(const SpbGeom* geom, const float* src_rgb, uint32_t* pack, void* stream) {
+    if (!geom || !src_rgb || !pack || geom->n_tiles < 1) return SPB_EINVAL;
+    k_build_tile_pack<<<(geom->n_tiles + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*geom, src_rgb, pack);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // unproject_kf_to_depths: dense exp((L + shift_b) * mask)
 // ------------------------------------------------------------------------------------------------

@@ -94,11 +94,12 @@ class LazyResult(dict):
 # ------------------------------------------------------------------------------------------------
 # shared launch helper: B pairs over one compact geometry
 # ------------------------------------------------------------------------------------------------
-def _launch_pairs(geom: CompactGeometry, src_rgb, trg_rgba, trg_Ks, poses, k, aff_src, aff_trg, tau,
+def _launch_pairs(geom: CompactGeometry, level, trg_rgba, trg_Ks, poses, k, aff_src, aff_trg, tau,
                   stats=None):
     """poses (B,4,4), trg_rgba (B,Hl,Wl,4), trg_Ks (B,3,3) or (3,3), aff_trg (B,2)|None.
     Returns out_pair (B,16), out_gk (B,N)."""
     lib = nat.lib()
+    src_rgb, pack = level
     B = poses.shape[0]
     dev = poses.device
     Hl, Wl = trg_rgba.shape[1], trg_rgba.shape[2]
@@ -113,6 +114,7 @@ def _launch_pairs(geom: CompactGeometry, src_rgb, trg_rgba, trg_Ks, poses, k, af
             p = pairs[i]
             p.trg_rgba = trg_rgba[j].data_ptr()
             p.src_rgb = src_rgb.data_ptr()
+            p.tile_pack = pack.data_ptr()
             p.K_trg = (trg_Ks[j] if trg_Ks.dim() == 3 else trg_Ks).data_ptr()
             p.pose = poses[j].data_ptr()
             p.k = k.data_ptr()
@@ -135,13 +137,13 @@ class _PairCost(torch.autograd.Function):
     """residual (B,) with gradients to k (N,), poses (B,4,4), aff_src (2,)|(1,2), aff_trg (2,)|(B,2)."""
 
     @staticmethod
-    def forward(ctx, k, poses, aff_src, aff_trg, geom, src_rgb, trg_rgba, trg_Ks, tau, check):
+    def forward(ctx, k, poses, aff_src, aff_trg, geom, level, trg_rgba, trg_Ks, tau, check):
         k_c = _f32c(k)
         poses_c = _f32c(poses)
         B = poses_c.shape[0]
         a_s = None if aff_src is None else _f32c(aff_src).reshape(-1)
         a_t = None if aff_trg is None else _f32c(aff_trg).reshape(-1, 2).expand(B, 2).contiguous()
-        out_pair, out_gk = _launch_pairs(geom, src_rgb, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau)
+        out_pair, out_gk = _launch_pairs(geom, level, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau)
         if check:
             # the reference asserts finiteness at five sites per call (core/dense_optim.py:44,78,311,
             # 321,340-343); one flag read (one sync) covers inputs and outputs here.  A NaN seed would
@@ -201,8 +203,9 @@ def _affine_pair(affine_comp):
 # ------------------------------------------------------------------------------------------------
 # statistics (slow path)
 # ------------------------------------------------------------------------------------------------
-def _point_stats(geom, src_image, src_rgb, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau, batch):
+def _point_stats(geom, src_image, level, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau, batch):
     dev = poses_c.device
+    src_rgb = level[0]
     B, P = poses_c.shape[0], geom.P
     src_pts = torch.empty((P, 3), dtype=torch.float32, device=dev)
     moved = torch.empty((B, P, 3), dtype=torch.float32, device=dev)
@@ -216,7 +219,7 @@ def _point_stats(geom, src_image, src_rgb, trg_rgba, trg_Ks, poses_c, k_c, a_s, 
         return nat.SpbStats(src_pts.data_ptr(), moved[done:].data_ptr(), trg_px[done:].data_ptr(),
                             raw[done:].data_ptr(), trg_ok[done:].data_ptr(), None, full[done:].data_ptr(), None)
 
-    _launch_pairs(geom, src_rgb, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau, stats=make)
+    _launch_pairs(geom, level, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau, stats=make)
     idx = geom.pad_index()
     src_ok = torch.empty(P, dtype=torch.uint8, device=dev)
     nat.check(nat.lib().spb_lift_points(geom.cref, k_c.data_ptr(), None, None, src_ok.data_ptr(), _stream()),
@@ -273,12 +276,12 @@ def photomeric_cost(src_keyframe, trg_keyframe, src_keypoint_logdepth, pose, cos
     Returns ``{'residual': (1,)}`` (+ statistics when ``collect_stats > 0``)."""
     collect_stats, check = _check_cfg(cost_config)
     geom = geometry_of(src_keyframe)
-    src_rgb = geom.source_samples(src_keyframe.image)
+    level = geom.level_buffers(src_keyframe.image)
     trg_rgba = pack_rgba(trg_keyframe.image)
     a_s, a_t = _affine_pair(affine_comp)
     trg_K = _f32c(trg_keyframe.K)
     tau = 1e-7
-    residual = _PairCost.apply(src_keypoint_logdepth, pose[None], a_s, a_t, geom, src_rgb, trg_rgba, trg_K, tau,
+    residual = _PairCost.apply(src_keypoint_logdepth, pose[None], a_s, a_t, geom, level, trg_rgba, trg_K, tau,
                                check)
     if collect_stats <= 0:
         return {'residual': residual}
@@ -292,7 +295,7 @@ def photomeric_cost(src_keyframe, trg_keyframe, src_keypoint_logdepth, pose, cos
 
     def produce():
         with torch.no_grad():
-            out = _point_stats(geom, src_image, src_rgb, trg_rgba, trg_K, poses_c, k_c, as_c, at_c, tau, False)
+            out = _point_stats(geom, src_image, level, trg_rgba, trg_K, poses_c, k_c, as_c, at_c, tau, False)
             if collect_stats > 1:
                 out.update(_keypoint_stats(geom, k_c, poses_c, trg_K, K_img, tau, False))
         return out
@@ -367,7 +370,7 @@ class _PointsCost(torch.autograd.Function):
         a_t = None if aff_trg is None else _f32c(aff_trg).reshape(-1)
         P = src_pts.shape[0]
         dev = pose_c.device
-        pr = nat.SpbPair(trg_rgba.data_ptr(), None, trg_K.data_ptr(), pose_c.data_ptr(), None, nat.ptr(a_s),
+        pr = nat.SpbPair(trg_rgba.data_ptr(), None, None, trg_K.data_ptr(), pose_c.data_ptr(), None, nat.ptr(a_s),
                          nat.ptr(a_t), 0, trg_rgba.shape[0], trg_rgba.shape[1], 1e-7)
         work = torch.empty(lib.spb_workspace_floats_points(P), dtype=torch.float32, device=dev)
         out_pair = torch.empty(nat.PAIR_NOUT, dtype=torch.float32, device=dev)

@@ -18,7 +18,7 @@ def photomeric_cost_batch(src_keyframe, trg_images, trg_Ks, src_keypoint_logdept
     """Returns ``{'residual': (B,)}`` (+ statistics when ``collect_stats > 0``)."""
     collect_stats, check = _check_cfg(cost_config)
     geom = geometry_of(src_keyframe)
-    src_rgb = geom.source_samples(src_keyframe.image)
+    level = geom.level_buffers(src_keyframe.image)
     trg_rgba = pack_rgba(trg_images)
     B = trg_rgba.shape[0]
     if poses.shape[0] != B:
@@ -28,7 +28,7 @@ def photomeric_cost_batch(src_keyframe, trg_images, trg_Ks, src_keypoint_logdept
     if Ks.dim() == 3 and Ks.shape[0] != B:
         raise AssertionError("one intrinsics matrix per target image expected")
     tau = 1e-6
-    residual = _PairCost.apply(src_keypoint_logdepth, poses, a_s, a_t, geom, src_rgb, trg_rgba, Ks, tau, check)
+    residual = _PairCost.apply(src_keypoint_logdepth, poses, a_s, a_t, geom, level, trg_rgba, Ks, tau, check)
     if collect_stats <= 0:
         return {'residual': residual}
     k_c = _f32c(src_keypoint_logdepth).clone()
@@ -39,7 +39,7 @@ def photomeric_cost_batch(src_keyframe, trg_images, trg_Ks, src_keypoint_logdept
 
     def produce():
         with torch.no_grad():
-            out = _point_stats(geom, src_image, src_rgb, trg_rgba, Ks, poses_c, k_c, as_c, at_c, tau, True)
+            out = _point_stats(geom, src_image, level, trg_rgba, Ks, poses_c, k_c, as_c, at_c, tau, True)
             if collect_stats > 1:
                 out.update(_keypoint_stats(geom, k_c, poses_c, Ks, Ks, tau, True))
         return out

@@ -126,22 +126,31 @@ class CompactGeometry:
         self.pad_index()
         return self._seg_ids
 
-    def source_samples(self, image):
-        """[3][n_pad] bilinear samples of the source level image at every point's own pixel
-        (cached per image tensor)."""
+    def level_buffers(self, image):
+        """(src_rgb, tile_pack) for a source level image, cached per image tensor:
+        src_rgb   [3][n_pad]  bilinear samples of the level image at every point's own pixel
+        tile_pack [n_tiles][PACK_WORDS] uint32, the tile-major {header, uv, logd, r, g, b} blocks the fused
+                  kernel streams with one bulk copy per tile"""
         key = (id(image), image._version, tuple(image.shape))
         hit = self._levels.get(key)
         if hit is not None and hit[0]() is image:
             self._levels.move_to_end(key)
-            return hit[1]
+            return hit[1], hit[2]
         img = _f32c(image[:3])
-        out = torch.empty((3, self.P_pad), dtype=torch.float32, device=img.device)
-        nat.check(nat.lib().spb_sample_source(self.cref, img.data_ptr(), img.shape[1], img.shape[2],
-                                              out.data_ptr(), _stream()), "spb_sample_source")
-        self._levels[key] = (weakref.ref(image), out)
+        lib = nat.lib()
+        src_rgb = torch.empty((3, self.P_pad), dtype=torch.float32, device=img.device)
+        nat.check(lib.spb_sample_source(self.cref, img.data_ptr(), img.shape[1], img.shape[2], src_rgb.data_ptr(),
+                                        _stream()), "spb_sample_source")
+        pack = torch.empty((self.n_tiles, nat.PACK_WORDS), dtype=torch.int32, device=img.device)
+        nat.check(lib.spb_build_tile_pack(self.cref, src_rgb.data_ptr(), pack.data_ptr(), _stream()),
+                  "spb_build_tile_pack")
+        self._levels[key] = (weakref.ref(image), src_rgb, pack)
         while len(self._levels) > 8:
             self._levels.popitem(last=False)
-        return out
+        return src_rgb, pack
+
+    def source_samples(self, image):
+        return self.level_buffers(image)[0]
 
     def bytes(self):
         return self.P_pad * 8 + self.n_tiles * 16 + self.N * 8

@@ -34,7 +34,8 @@ class AlignmentBatch:
 
     problems: list of dicts with keys
         geom      CompactGeometry of the source keyframe (may be shared between problems)
-        src_rgb   [3][n_pad] cached source samples at the level (``geom.source_samples(image)``)
+        src_rgb   [3][n_pad] cached source samples at the level   } ``geom.level_buffers(image)``
+        pack      [n_tiles][PACK_WORDS] tile-major level buffer   }
         trg_rgba  (Hl,Wl,4) packed target level image
         K_trg     (3,3) target intrinsics
         pose      (4,4) initial source->target transform
@@ -80,7 +81,7 @@ class AlignmentBatch:
                                     for p in problems]).contiguous()
         self.aff_trg = torch.stack([_f32c(p.get('aff_trg', zero2) if p.get('aff_trg') is not None else zero2)
                                     for p in problems]).contiguous()
-        self._keep = [(p['src_rgb'], p['trg_rgba']) for p in problems]
+        self._keep = [(p['src_rgb'], p['trg_rgba'], p['pack']) for p in problems]
         use_aff = self.with_affine or any(p.get('aff_src') is not None for p in problems)
         self.use_affine = use_aff
         # descriptor arrays
@@ -92,6 +93,7 @@ class AlignmentBatch:
             q = parr[i]
             q.trg_rgba = p['trg_rgba'].data_ptr()
             q.src_rgb = p['src_rgb'].data_ptr()
+            q.tile_pack = p['pack'].data_ptr()
             q.K_trg = self.K_trg[i].data_ptr()
             q.pose = self.poses[i].data_ptr()
             q.k = self.k.data_ptr() + 4 * int(seg_off[i])
@@ -197,7 +199,7 @@ class AlignmentBatch:
     def algorithmic_bytes_per_iter(self, gn=True):
         """per pair 24 P + 4 C Hl Wl + outputs (C = 3)."""
         total = 0
-        for i, (src_rgb, trg) in enumerate(self._keep):
+        for i, (src_rgb, trg, _pack) in enumerate(self._keep):
             P = self._P[i]
             Hl, Wl = trg.shape[0], trg.shape[1]
             N = int(self.seg_cnt_host[i])
@@ -210,7 +212,7 @@ def make_problem(src_kf, trg_image, trg_K, pose, k, geom=None, aff_src=None, aff
     """Convenience: build one problem dict from a source keyframe (dense) and a planar target image."""
     if geom is None:
         geom = CompactGeometry(src_kf.keypoint_regions, src_kf.get_logdepth(), src_kf.keypoints, src_kf.K)
-    src_rgb = geom.source_samples(src_kf.image)
+    src_rgb, pack = geom.level_buffers(src_kf.image)
     trg_rgba = pack_rgba(trg_image)[0]
-    return dict(geom=geom, src_rgb=src_rgb, trg_rgba=trg_rgba, K_trg=trg_K, pose=pose, k=k,
+    return dict(geom=geom, src_rgb=src_rgb, pack=pack, trg_rgba=trg_rgba, K_trg=trg_K, pose=pose, k=k,
                 aff_src=aff_src, aff_trg=aff_trg, tau=tau)

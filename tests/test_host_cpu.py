@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     from super_primitive_b200 import _native
     assert ctypes.sizeof(_native.SpbGeom) == 6 * 8 + 6 * 4
-    assert ctypes.sizeof(_native.SpbPair) == 7 * 8 + 4 * 4
+    assert ctypes.sizeof(_native.SpbPair) == 8 * 8 + 4 * 4
     assert ctypes.sizeof(_native.SpbStats) == 8 * 8
 
 
