@@ -150,7 +150,11 @@ int64_t spb_workspace_floats_points(int P);
  *   max_tiles : max over problems of geom.n_tiles (grid sizing)
  *   out_pair  : [n_pairs][SPB_GN_PAIR_NOUT]   out_seg : [seg_total][SPB_GN_SEG_NOUT]
  *   seg_off   : [n_pairs] offset of each problem's segments in out_seg
- *   ev_before / ev_after : optional cudaEvent_t recorded around the fused kernel alone (NULL = off) */
+ *   with_affine : 0 = pairs carry no brightness terms; 1 = optimise the target affine (8 pose columns);
+ *                 2 = brightness terms present but held fixed (6 pose columns)
+ *   ev_before / ev_after : optional cudaEvent_t recorded around the fused kernel alone (NULL = off)
+ * Points whose transformed depth lies within the guarded-reciprocal band |Yz| <= 1e-6 are treated as invalid in
+ * GN mode (the gradient mode reproduces the reference's clamped-reciprocal behaviour exactly). */
 int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off,
                       int n_pairs, int max_tiles, float irls_eps, int with_affine, float* work,
                       int64_t work_stride, float* out_pair, float* out_seg, void* ev_before,

@@ -445,14 +445,16 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
         for (int j = 0; j < SPB_PPT; ++j) {
             const int i = j * 32 + lane;
             Proj q;
-            if (project_point(c, s_uv[i], s_f[SPB_TILE + i], shift, Wl, q)) {
+            bool ok = project_point(c, s_uv[i], s_f[SPB_TILE + i], shift, Wl, q);
+            if constexpr (PACKED) ok = ok && q.live;       // see point_gn6_packed
+            if (ok) {
                 Taps4 tp;
                 load_taps(trg, Wl, q.off, tp);
                 const float i0 = s_f[2 * SPB_TILE + i], i1 = s_f[3 * SPB_TILE + i], i2 = s_f[4 * SPB_TILE + i];
                 if constexpr (MODE == MODE_GRAD)
                     point_grad<AFF>(c, tp, q, i0, i1, i2, acc, seg[0]);
                 else if constexpr (PACKED)
-                    point_gn6_packed(c, tp, q, i0, i1, i2, irls_eps, pacc, pseg);
+                    point_gn6_packed<AFF>(c, tp, q, i0, i1, i2, irls_eps, pacc, pseg);
                 else
                     point_gn<NP, NACC, NSEG>(c, tp, q, i0, i1, i2, irls_eps, acc, seg);
             }
@@ -776,26 +778,31 @@ extern "C" int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, con
     if (n_pairs > 65535) return SPB_ELIMIT;
     cudaStream_t st = (cudaStream_t)stream;
     const int ctas = ctas_for(max_tiles, n_pairs);
-    const int nacc = with_affine ? Sizes<MODE_GN, 8>::NACC : Sizes<MODE_GN, 6>::NACC;
-    const int nseg = with_affine ? Sizes<MODE_GN, 8>::NSEG : Sizes<MODE_GN, 6>::NSEG;
+    // with_affine: 0 = no brightness terms, 1 = optimise the target affine (8 pose columns),
+    //              2 = brightness terms present but fixed (6 pose columns)
+    const bool np8 = with_affine == 1;
+    const int nacc = np8 ? Sizes<MODE_GN, 8>::NACC : Sizes<MODE_GN, 6>::NACC;
+    const int nseg = np8 ? Sizes<MODE_GN, 8>::NSEG : Sizes<MODE_GN, 6>::NSEG;
     if (work_stride < (int64_t)ctas * nacc + (int64_t)max_tiles * nseg) return SPB_EINVAL;
     dim3 grid(ctas, n_pairs);
     if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
-    if (with_affine) {
-        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GN, 8, true>);
-        if (e != cudaSuccess) return (int)e;
+    cudaError_t e;
+    if (np8) {
+        if ((e = allow_dyn_smem(k_align_global<MODE_GN, 8, true>)) != cudaSuccess) return (int)e;
         k_align_global<MODE_GN, 8, true><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, irls_eps, work, work_stride);
-        SPB_CHECK_LAUNCH();
-        if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
-        k_finalize_gn<8><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
-    } else {
-        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GN, 6, true>);
-        if (e != cudaSuccess) return (int)e;
+    } else if (with_affine == 2) {
+        if ((e = allow_dyn_smem(k_align_global<MODE_GN, 6, true>)) != cudaSuccess) return (int)e;
         k_align_global<MODE_GN, 6, true><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, irls_eps, work, work_stride);
-        SPB_CHECK_LAUNCH();
-        if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
-        k_finalize_gn<6><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
+    } else {
+        if ((e = allow_dyn_smem(k_align_global<MODE_GN, 6, false>)) != cudaSuccess) return (int)e;
+        k_align_global<MODE_GN, 6, false><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, irls_eps, work, work_stride);
     }
+    SPB_CHECK_LAUNCH();
+    if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
+    if (np8)
+        k_finalize_gn<8><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
+    else
+        k_finalize_gn<6><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

@@ -137,7 +137,8 @@ __device__ __forceinline__ bool project_point(const float* __restrict__ c, uint3
     q.yb = q.Yy * q.rho;
     const float xn = fmaf(q.xb, pa.x, pa.y);
     const float yn = fmaf(q.yb, pa.z, pa.w);
-    const bool ok = (w >> 31) && (z > 1e-7f) && (fabsf(xn) <= 0.99f) && (fabsf(yn) <= 0.99f) && (q.Yz > pb.z);
+    // |xn| <= .99 && |yn| <= .99 && Yz > tau && z > 1e-7 && src_ok, folded into two compares
+    const bool ok = (w >> 31) && (fmaxf(fabsf(xn), fabsf(yn)) <= 0.99f) && (fminf(q.Yz - pb.z, z - 1e-7f) > 0.0f);
     const float ix = fmaf(xn, pb.x, pb.x);
     const float iy = fmaf(yn, pb.y, pb.y);
     const float fxf = floorf(ix), fyf = floorf(iy);

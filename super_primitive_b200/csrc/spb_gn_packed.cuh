@@ -18,11 +18,11 @@ struct GnAcc6 {            // upper triangle of the 6x6 pose block, g_p, cost te
     float2 a44;            // (4,4)(4,5)
     float a55;
     float2 g01, g23, g45;
-    float cost, wcost, nv;
+    float cost;            // sum |r| ; the weighted cost and the valid count are not accumulated on this path
     __device__ __forceinline__ void zero() {
         const float2 z = make_float2(0.f, 0.f);
         a00 = a02 = a04 = a12 = a14 = a22 = a24 = a34 = a44 = g01 = g23 = g45 = z;
-        a11 = a33 = a55 = cost = wcost = nv = 0.f;
+        a11 = a33 = a55 = cost = 0.f;
     }
     __device__ __forceinline__ void store(float (&o)[30]) const {
         o[0] = a00.x; o[1] = a00.y; o[2] = a02.x; o[3] = a02.y; o[4] = a04.x; o[5] = a04.y;
@@ -31,7 +31,7 @@ struct GnAcc6 {            // upper triangle of the 6x6 pose block, g_p, cost te
         o[15] = a33; o[16] = a34.x; o[17] = a34.y;
         o[18] = a44.x; o[19] = a44.y; o[20] = a55;
         o[21] = g01.x; o[22] = g01.y; o[23] = g23.x; o[24] = g23.y; o[25] = g45.x; o[26] = g45.y;
-        o[27] = cost; o[28] = wcost; o[29] = nv;
+        o[27] = cost; o[28] = 0.f; o[29] = 0.f;
     }
 };
 
@@ -63,6 +63,9 @@ __device__ __forceinline__ void blend2(float nw, float ne, float sw, float se, f
     d.x = fmaf(fy, d1 - d0, d0);
 }
 
+// Precondition: q.live (callers treat points behind the guarded-reciprocal threshold |Yz| <= 1e-6 as invalid on
+// this path -- a sub-micrometre depth regime where the reference itself samples with a clamped reciprocal).
+template <bool AFF>
 __device__ __forceinline__ void point_gn6_packed(const float* __restrict__ c, const Taps4& tp, const Proj& q,
                                                  float Is0, float Is1, float Is2, float irls_eps, GnAcc6& A,
                                                  GnSeg6& S) {
@@ -75,15 +78,14 @@ __device__ __forceinline__ void point_gn6_packed(const float* __restrict__ c, co
     const float ea = c[F_EA], bb = c[F_BB];
     // GA = (Guu, Guv), GB = (Guv, Gvv), H = (hu, hv): image-gradient moments over the channels
     float2 GA = make_float2(0.f, 0.f), GB = GA, H = GA;
-    float cost = 0.f, wcost = 0.f;
+    float cost = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        const float r = Is[ch] - fmaf(ea, I[ch], bb);
+        const float r = AFF ? (Is[ch] - fmaf(ea, I[ch], bb)) : (Is[ch] - I[ch]);
         const float ar = fabsf(r);
         const float wgt = __fdividef(1.0f, fmaxf(ar, irls_eps));     // IRLS weight of the L1 objective
         const float wr = wgt * r;
         cost += ar;
-        wcost = fmaf(wr, r, wcost);
         const float2 wd = mul2(wgt, d[ch]);                          // (w dIx, w dIy)
         GA = fma2(wd.x, d[ch], GA);
         GB = fma2(wd.y, d[ch], GB);
@@ -96,24 +98,13 @@ __device__ __forceinline__ void point_gn6_packed(const float* __restrict__ c, co
 
     // mu = d x_/d(xi,k), mv = d y_/d(xi,k) with mu0 = rho, mu1 = 0, mv0 = 0, mv1 = rho
     const float rho = q.rho, xb = q.xb, yb = q.yb;
-    float2 mu23, mu45, mv23, mv45;
-    float mu6, mv6;
-    if (q.live) {
-        const float xy = xb * yb;
-        mu23 = make_float2(-rho * xb, -xy);
-        mu45 = make_float2(fmaf(xb, xb, 1.0f), -yb);
-        mv23 = make_float2(-rho * yb, -fmaf(yb, yb, 1.0f));
-        mv45 = make_float2(xy, xb);
-        mu6 = rho * fmaf(xb, c[F_TR(2)], -c[F_TR(0)]);
-        mv6 = rho * fmaf(yb, c[F_TR(2)], -c[F_TR(1)]);
-    } else {                                         // constant reciprocal: no z-derivative (never taken in practice)
-        mu23 = make_float2(0.f, 0.f);
-        mu45 = make_float2(rho * q.Yz, -rho * q.Yy);
-        mv23 = make_float2(0.f, -rho * q.Yz);
-        mv45 = make_float2(0.f, rho * q.Yx);
-        mu6 = rho * (q.Yx - c[F_TR(0)]);
-        mv6 = rho * (q.Yy - c[F_TR(1)]);
-    }
+    const float xy = xb * yb;
+    const float2 mu23 = make_float2(-rho * xb, -xy);
+    const float2 mu45 = make_float2(fmaf(xb, xb, 1.0f), -yb);
+    const float2 mv23 = make_float2(-rho * yb, -fmaf(yb, yb, 1.0f));
+    const float2 mv45 = make_float2(xy, xb);
+    const float mu6 = rho * fmaf(xb, c[F_TR(2)], -c[F_TR(0)]);
+    const float mv6 = rho * fmaf(yb, c[F_TR(2)], -c[F_TR(1)]);
     // pu = Guu mu + Guv mv ; pv = Guv mu + Gvv mv
     const float2 pu01 = mul2(rho, GA);                               // (Guu rho, Guv rho)
     const float pv1 = Gvv * rho;
@@ -139,8 +130,6 @@ __device__ __forceinline__ void point_gn6_packed(const float* __restrict__ c, co
     A.g23 = fma2(hu, mu23, fma2(hv, mv23, A.g23));
     A.g45 = fma2(hu, mu45, fma2(hv, mv45, A.g45));
     A.cost += cost;
-    A.wcost += wcost;
-    A.nv += 1.0f;
     // depth column of this tile's segment
     S.b01 = fma2(rho, p6, S.b01);
     S.b23 = fma2(p6.x, mu23, fma2(p6.y, mv23, S.b23));

@@ -128,7 +128,8 @@ class AlignmentBatch:
         e0, e1 = (None, None) if ev is None else (ev[0].cuda_event, ev[1].cuda_event)
         nat.check(nat.lib().spb_gn_accumulate(self.d_geoms.data_ptr(), self.d_pairs.data_ptr(),
                                               self.d_seg_off.data_ptr(), self.n, self.max_tiles, self.irls_eps,
-                                              1 if self.with_affine else 0, self.work.data_ptr(), self.work_stride,
+                                              1 if self.with_affine else (2 if self.use_affine else 0),
+                                              self.work.data_ptr(), self.work_stride,
                                               self.gn_pair.data_ptr(), self.gn_seg.data_ptr(), e0, e1, _stream()),
                   "spb_gn_accumulate")
         self.launches += 2
