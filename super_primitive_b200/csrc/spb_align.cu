@@ -420,6 +420,8 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
     GnAcc6 pacc;
     pacc.zero();
+    GradAcc gacc;
+    gacc.zero();
 
     int slot = 0, fill = SPB_WSTAGES - 1;                  // slot consumed now / slot refilled now
     uint32_t phase = 0;
@@ -452,7 +454,7 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
                 load_taps(trg, Wl, q.off, tp);
                 const float i0 = s_f[2 * SPB_TILE + i], i1 = s_f[3 * SPB_TILE + i], i2 = s_f[4 * SPB_TILE + i];
                 if constexpr (MODE == MODE_GRAD)
-                    point_grad<AFF>(c, tp, q, i0, i1, i2, acc, seg[0]);
+                    point_grad_packed<AFF>(c, tp, q, i0, i1, i2, gacc, seg[0]);
                 else if constexpr (PACKED)
                     point_gn6_packed<AFF>(c, tp, q, i0, i1, i2, irls_eps, pacc, pseg);
                 else
@@ -466,6 +468,7 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
         if (++slot == SPB_WSTAGES) { slot = 0; phase ^= 1u; }
     }
     if constexpr (PACKED) pacc.store(acc);
+    if constexpr (MODE == MODE_GRAD) gacc.store(acc);
     __syncthreads();
     block_reduce_store<NACC>(acc, s_red, part_pair + (size_t)blockIdx.x * NACC);
 }

@@ -137,3 +137,62 @@ __device__ __forceinline__ void point_gn6_packed(const float* __restrict__ c, co
     S.d = fmaf(mu6, p6.x, fmaf(mv6, p6.y, S.d));
     S.gd = fmaf(mu6, hu, fmaf(mv6, hv, S.gd));
 }
+
+// ---- gradient mode, packed ------------------------------------------------------------------------
+// canonical order (SPB_PAIR_NOUT): cost, gt[3], gM rows (3x3), ga, gb, nvalid
+struct GradAcc {
+    float cost;
+    float2 gt01;
+    float gt2;
+    float2 m00;  float m02;     // row 0 of d cost / d M
+    float2 m10;  float m12;
+    float2 m20;  float m22;
+    float ga, gb, nv;
+    __device__ __forceinline__ void zero() {
+        const float2 z = make_float2(0.f, 0.f);
+        gt01 = m00 = m10 = m20 = z;
+        cost = gt2 = m02 = m12 = m22 = ga = gb = nv = 0.f;
+    }
+    __device__ __forceinline__ void store(float (&o)[16]) const {
+        o[0] = cost; o[1] = gt01.x; o[2] = gt01.y; o[3] = gt2;
+        o[4] = m00.x; o[5] = m00.y; o[6] = m02; o[7] = m10.x; o[8] = m10.y; o[9] = m12;
+        o[10] = m20.x; o[11] = m20.y; o[12] = m22; o[13] = ga; o[14] = gb; o[15] = nv;
+    }
+};
+
+template <bool AFF>
+__device__ __forceinline__ void point_grad_packed(const float* __restrict__ c, const Taps4& tp, const Proj& q,
+                                                  float Is0, float Is1, float Is2, GradAcc& A, float& gk) {
+    float I[3];
+    float2 d[3];
+    blend2(tp.nw.x, tp.ne.x, tp.sw.x, tp.se.x, q.fx, q.fy, I[0], d[0]);
+    blend2(tp.nw.y, tp.ne.y, tp.sw.y, tp.se.y, q.fx, q.fy, I[1], d[1]);
+    blend2(tp.nw.z, tp.ne.z, tp.sw.z, tp.se.z, q.fx, q.fy, I[2], d[2]);
+    const float Is[3] = {Is0, Is1, Is2};
+    float2 gxy = make_float2(0.f, 0.f);            // sum_c sign(r_c) (dIx_c, dIy_c)
+    float ga = 0.f, gb = 0.f, cost = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float r = AFF ? (Is[ch] - fmaf(c[F_EA], I[ch], c[F_BB])) : (Is[ch] - I[ch]);
+        cost += fabsf(r);
+        const float s = (r > 0.f) ? 1.0f : ((r < 0.f) ? -1.0f : 0.0f);
+        gxy = fma2(s, d[ch], gxy);
+        if (AFF) { ga = fmaf(s, I[ch], ga); gb += s; }
+    }
+    // d cost / d (x_, y_) = (cu gx, cv gy);  gY = rho (gx_, gy_, -(gx_ x_ + gy_ y_))
+    const float2 gb2 = __fmul2_rn(gxy, *reinterpret_cast<const float2*>(c + F_CU));
+    const float2 gY = mul2(q.rho, gb2);
+    const float gYz = q.live ? -fmaf(gY.x, q.xb, gY.y * q.yb) : 0.0f;
+    const float2 zuv = mul2(q.zs, make_float2(q.uc, q.vc));
+    A.cost += cost;
+    A.gt01 = __fadd2_rn(A.gt01, gY);
+    A.gt2 += gYz;
+    A.m00 = fma2(gY.x, zuv, A.m00);  A.m02 = fmaf(gY.x, q.zs, A.m02);
+    A.m10 = fma2(gY.y, zuv, A.m10);  A.m12 = fmaf(gY.y, q.zs, A.m12);
+    A.m20 = fma2(gYz, zuv, A.m20);   A.m22 = fmaf(gYz, q.zs, A.m22);
+    if (AFF) { A.ga = fmaf(c[F_EA], ga, A.ga); A.gb -= gb; }
+    A.nv += 1.0f;
+    // d cost / d k_b = gY . (R X) = gY . Y - gY . t, and gY . Y == 0 when the reciprocal is live
+    gk -= fmaf(gY.x, c[F_TR(0)], fmaf(gY.y, c[F_TR(1)], gYz * c[F_TR(2)]));
+    if (!q.live) gk += fmaf(gY.x, q.Yx, gY.y * q.Yy);
+}
