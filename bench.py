@@ -324,6 +324,28 @@ def main():
     pairs_total = args.pairs * world
     value = pairs_total * steps / (total_ms * 1e-3)
 
+    # ---- the other iteration kind, same batch, reported alongside ("report both, labelled") --------
+    other = None
+    other_fn = batch.grad_step if args.mode == "gn" else batch.gn_step
+    oev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in oev:
+        a.record()
+        b.record()
+    for _ in range(warm):
+        other_fn()
+    barrier()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    for i in range(steps):
+        other_fn(oev[i])
+    o1.record()
+    barrier()
+    ot = torch.tensor([o0.elapsed_time(o1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ot, op=dist.ReduceOp.MAX)
+    other_ms = float(ot.item())
+    other_kern_ms = float(np.mean([a.elapsed_time(b) for a, b in oev]))
+
     # ---- end-to-end arm: host buffers in, results out, every step -------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -395,6 +417,12 @@ def main():
                              "kernel": "k_align_global<GN>" if args.mode == "gn" else "k_align_global<GRAD>",
                              "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": int(alg_bytes)},
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        o_bytes = batch.algorithmic_bytes_per_iter(gn=(args.mode != "gn"))
+        line["other_iteration"] = {
+            "iteration": "cost + first-order gradient (what the reference's backward() yields)" if args.mode == "gn"
+            else "IRLS Gauss-Newton/LM",
+            "value": pairs_total * steps / (other_ms * 1e-3), "unit": UNIT, "ms_per_step": other_ms / steps,
+            "kernel_ms": other_kern_ms, "roofline_frac": o_bytes / (other_kern_ms * 1e-3) / 1e9 / peak}
         if gather_ms is not None:
             line["final_gather_ms"] = gather_ms
         print(json.dumps(line), flush=True)

@@ -460,28 +460,6 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
                 else
                     point_gn<NP, NACC, NSEG>(c, tp, q, i0, i1, i2, irls_eps, acc, seg);
             }
-#if SPB_PREFETCH
-            // Half-way through the tile the NEXT tile's block has normally landed in the other ring slot: every
-            // lane projects one proxy point of it (points 4*lane .. cover all its rows) and pulls the two texel
-            // rows it will sample into L2, so the next tile's gathers see L2 latency instead of DRAM latency.
-            if (j == SPB_PPT / 2 - 1 && t + WS < g.n_tiles) {
-                const int nslot = (slot + 1 == SPB_WSTAGES) ? 0 : slot + 1;
-                const uint32_t nphase = (slot + 1 == SPB_WSTAGES) ? (phase ^ 1u) : phase;
-                if (mbar_test(smem_u32(bars + nslot), nphase)) {
-                    const uint32_t* nsl = ring + nslot * SPB_SLOT_WORDS;
-                    const int nseg_i = (int)nsl[0];
-                    const float nshift = (nseg_i < SPB_NSHIFT) ? s_shift[nseg_i]
-                                                                : (__ldg(pr.k + nseg_i) - __ldg(g.seg_lkp + nseg_i));
-                    Proj pq;
-                    const int pi = 4 * lane;
-                    if (project_point(c, nsl[4 + pi], reinterpret_cast<const float*>(nsl + 4)[SPB_TILE + pi], nshift, Wl,
-                                      pq)) {
-                        prefetch_l2(trg + pq.off);
-                        prefetch_l2(trg + pq.off + Wl);
-                    }
-                }
-            }
-#endif
         }
         if constexpr (PACKED) pseg.store(seg);
         tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);

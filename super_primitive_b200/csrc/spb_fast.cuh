@@ -21,9 +21,6 @@
 #ifndef SPB_PIPE
 #define SPB_PIPE 1                             // points per lane whose taps are in flight (1 or 2)
 #endif
-#ifndef SPB_PREFETCH
-#define SPB_PREFETCH 1                         // L2-prefetch the next tile's target footprint (proxy points)
-#endif
 #ifndef SPB_WSTAGES
 #define SPB_WSTAGES 2                          // ring slots per warp
 #endif
@@ -150,22 +147,6 @@ __device__ __forceinline__ bool project_point(const float* __restrict__ c, uint3
     q.off = (int)fyf * Wl + (int)fxf;
     return ok;
 }
-
-// non-blocking probe of an mbarrier phase
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // the four RGBA taps of one point; issued early (software pipelining), consumed by point_grad / point_gn
 struct Taps4 {
