@@ -198,6 +198,11 @@ int spb_dense_depths(const uint8_t* masks, const float* logd, int64_t logd_seg_s
 int spb_depth_splat(const SpbGeom* geom, const float* k, const float* pose /* NULL = identity */,
                     int mean, unsigned long long* keys, float* sum, float* out, void* stream);
 
+/* estimate_depth_diff (core/ops.py:59-96) for an arbitrary point cloud pts [P][3] already in the target frame:
+ * same splat semantics as spb_depth_splat; valid [P] (may be NULL) receives the reference's `valid_depth` mask. */
+int spb_depth_splat_points(const float* pts, int P, const float* K, int H, int W, int mean,
+                           unsigned long long* keys, float* sum, float* out, uint8_t* valid, void* stream);
+
 /* lifted points of a keyframe: src_pts [n][3] (core/dense_optim.py:176-200) */
 int spb_lift_points(const SpbGeom* geom, const float* k, float* src_pts, int64_t* seg_ids,
                     uint8_t* src_ok, void* stream);

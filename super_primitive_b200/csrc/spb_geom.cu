@@ -367,4 +367,55 @@ extern "C" int spb_depth_splat(const SpbGeom* geom, const float* k, const float*
     return SPB_OK;
 }
 
-extern "C" int spb_version(void) { return 100; }
+// estimate_depth_diff for arbitrary points (core/ops.py:59-96): same splat as k_lift<true>, input (P,3)
+__global__ void k_splat_points(const float* __restrict__ pts, int P, const float* __restrict__ K, int H, int W,
+                               int mean, unsigned long long* __restrict__ keys, float* __restrict__ sum,
+                               uint8_t* __restrict__ valid) {
+    const float fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < P; q += gridDim.x * blockDim.x) {
+        const float X = pts[3 * (size_t)q], Y = pts[3 * (size_t)q + 1], Z = pts[3 * (size_t)q + 2];
+        const float zi = fabsf(Z) > 1e-6f ? 1.0f / Z : 1e-6f;
+        const float up = fmaf(X * fx, zi, cx), vp = fmaf(Y * fy, zi, cy);
+        bool ok = (Z > 1e-6f) && isfinite(up) && isfinite(vp) && fabsf(up) < 1e6f && fabsf(vp) < 1e6f;
+        int col = 0, row = 0;
+        if (ok) {
+            col = (int)up; row = (int)vp;                     // .long() truncation toward zero
+            ok = row >= 0 && row < H && col >= 0 && col < W;
+        }
+        if (valid) valid[q] = ok ? 1 : 0;
+        if (!ok) continue;
+        const int idx = row * W + col;
+        if (mean) {
+            atomicAdd(sum + idx, Z);
+            atomicAdd(keys + idx, 1ull);
+        } else {
+            atomicMax(keys + idx, ((unsigned long long)(q + 1) << 32) | __float_as_uint(Z));
+        }
+    }
+}
+
+extern "C" int spb_depth_splat_points(const float* pts, int P, const float* K, int H, int W, int mean,
+                                      unsigned long long* keys, float* sum, float* out, uint8_t* valid,
+                                      void* stream) {
+    if (!pts || P < 1 || !K || H < 1 || W < 1 || !keys || !out) return SPB_EINVAL;
+    if (mean && !sum) return SPB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = H * W;
+    cudaError_t e = cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)HW, st);
+    if (e != cudaSuccess) return (int)e;
+    if (mean) {
+        e = cudaMemsetAsync(sum, 0, sizeof(float) * (size_t)HW, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    int bx = (P + 255) / 256;
+    if (bx > 148 * 8) bx = 148 * 8;
+    k_splat_points<<<bx, 256, 0, st>>>(pts, P, K, H, W, mean, keys, sum, valid);
+    SPB_CHECK_LAUNCH();
+    int br = (HW + 255) / 256;
+    if (br > 148 * 8) br = 148 * 8;
+    k_splat_resolve<<<br, 256, 0, st>>>(keys, sum, mean, HW, out);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+extern "C" int spb_version(void) { return 101; }
