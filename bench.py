@@ -266,6 +266,41 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def time_dropin_single_pair(device, iters=60, warm=10):
+    """photomeric_cost (collect_stats=0) -> residual.mean().backward() -> Adam.step on one C2 pair through
+    super_primitive_b200.dense_optim, i.e. exactly what odometery/two_frame_sfm.py does per iteration."""
+    from super_primitive_b200 import dense_optim as do, synthetic as syn
+    H, W, N = WORKLOAD["H"], WORKLOAD["W"], WORKLOAD["N"]
+    src, trg, k0, pose0 = syn.two_frame_problem(H, W, N, kind=WORKLOAD["kind"], seed=0, noise=0.01)
+    src, trg = src.to(device), trg.to(device)
+    k = torch.nn.Parameter(k0.to(device))
+    pose = torch.nn.Parameter(pose0.to(device))
+    opt = torch.optim.Adam([{'params': [k], 'lr': 1e-3}, {'params': [pose], 'lr': 1e-2}], lr=1e-3)
+    cfg = {'mode': 'colour', 'collect_stats': 0}
+
+    def one():
+        loss = do.photomeric_cost(src, trg, k, pose, cfg)['residual'].mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    for _ in range(warm):
+        one()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(iters):
+        one()
+    b.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    return {"iters_per_s": iters / wall, "ms_per_iter_wall": wall / iters * 1e3,
+            "ms_per_iter_device": a.elapsed_time(b) / iters,
+            "what": "reference loop through the drop-in API on ONE pair (forward+backward kernel, finiteness check "
+                    "= 1 host sync, Adam.step); host/launch-bound"}
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -368,6 +403,12 @@ def main():
                "what": "per step: H2D (pinned) of compact geometry + cached source samples + target image + pose + "
                        "seeds for every pair, one GN/LM iteration, D2H of poses, seeds and LM state"}
 
+    # ---- drop-in arm: the reference's own loop (photomeric_cost -> backward -> Adam.step) through the public
+    #      Python surface, ONE pair, device-resident inputs: launch/host-bound, reported for context -------------
+    dropin = None
+    if rank == 0 and not args.no_e2e:
+        dropin = time_dropin_single_pair(device)
+
     # ---- the only collective of the path: final gather of poses / seeds / cost -------------------------
     gather_ms = None
     if world > 1:
@@ -423,6 +464,8 @@ def main():
             else "IRLS Gauss-Newton/LM",
             "value": pairs_total * steps / (other_ms * 1e-3), "unit": UNIT, "ms_per_step": other_ms / steps,
             "kernel_ms": other_kern_ms, "roofline_frac": o_bytes / (other_kern_ms * 1e-3) / 1e9 / peak}
+        if dropin is not None:
+            line["dropin_single_pair"] = dropin
         if gather_ms is not None:
             line["final_gather_ms"] = gather_ms
         print(json.dumps(line), flush=True)
