@@ -394,13 +394,8 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     __syncthreads();
     const float* c = s_ctx;
 
-    // every warp walks a CONTIGUOUS run of tiles [t_begin, t_end): consecutive tiles mostly belong to the same
-    // segment, so the per-segment partial sums stay in registers and are reduced + stored only when the
-    // segment changes (tiles that did not flush store zeros; k_finalize_* sums all tile slots of a segment)
-    const int n_warps_pair = gridDim.x * SPB_WARPS;
-    const int run = (g.n_tiles + n_warps_pair - 1) / n_warps_pair;
-    const int t_begin = (blockIdx.x * SPB_WARPS + warp) * run;
-    const int t_end = min(t_begin + run, g.n_tiles);
+    const int WS = gridDim.x * SPB_WARPS;                  // tile stride of this warp
+    const int t_first = blockIdx.x * SPB_WARPS + warp;
     const uint32_t* pack = pr.tile_pack;
 
     // producer (lane 0): ONE bulk copy brings the whole tile block (header + uv + logd + r + g + b)
@@ -412,8 +407,8 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < SPB_WSTAGES - 1; ++s) {
-            const int t = t_begin + s;
-            if (t < t_end) issue(t, s);
+            const int t = t_first + s * WS;
+            if (t < g.n_tiles) issue(t, s);
         }
     }
 
@@ -427,41 +422,27 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     pacc.zero();
     GradAcc gacc;
     gacc.zero();
-    float seg[NSEG];
-#pragma unroll
-    for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
-    GnSeg6 pseg;
-    pseg.zero();
 
     int slot = 0, fill = SPB_WSTAGES - 1;                  // slot consumed now / slot refilled now
     uint32_t phase = 0;
-    int cur_seg = -1, prev_t = -1;                         // segment whose partials are in registers, its last tile
-    auto flush = [&](int t_store) {                        // reduce the pending per-segment partials into tile t_store
-        if constexpr (PACKED) pseg.store(seg);
-        tile_reduce_store<NSEG>(seg, part_seg + (size_t)t_store * NSEG, lane);
-#pragma unroll
-        for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
-        pseg.zero();
-    };
-    for (int t = t_begin; t < t_end; ++t) {
+    for (int t = t_first; t < g.n_tiles; t += WS) {
         if (lane == 0) {
-            const int tn = t + (SPB_WSTAGES - 1);
-            if (tn < t_end) issue(tn, fill);
+            const int tn = t + (SPB_WSTAGES - 1) * WS;
+            if (tn < g.n_tiles) issue(tn, fill);
         }
         mbar_wait(smem_u32(bars + slot), phase);
         const uint32_t* sl = ring + slot * SPB_SLOT_WORDS;
-        const int sidx = (int)sl[0];
-        if (sidx != cur_seg) {                             // warp-uniform
-            if (cur_seg >= 0) flush(prev_t);
-            cur_seg = sidx;
-        } else if (lane < NSEG) {
-            part_seg[(size_t)prev_t * NSEG + lane] = 0.f;  // previous tile of the same segment contributes nothing
-        }
-        prev_t = t;
+        const int sidx = (int)sl[0], cnt = (int)sl[1];
         const float shift = (sidx < SPB_NSHIFT) ? s_shift[sidx] : (__ldg(pr.k + sidx) - __ldg(g.seg_lkp + sidx));
         const uint32_t* s_uv = sl + 4;
         const float* s_f = reinterpret_cast<const float*>(sl + 4);
+        float seg[NSEG];
+#pragma unroll
+        for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
+        GnSeg6 pseg;
+        pseg.zero();
         // padding entries of a partial tile are zero words: uv bit 31 clear => invalid, no bounds test needed
+        (void)cnt;
         SPB_PRAGMA_UNROLL(SPB_UNROLL)
         for (int j = 0; j < SPB_PPT; ++j) {
             const int i = j * 32 + lane;
@@ -480,11 +461,12 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
                     point_gn<NP, NACC, NSEG>(c, tp, q, i0, i1, i2, irls_eps, acc, seg);
             }
         }
+        if constexpr (PACKED) pseg.store(seg);
+        tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
         __syncwarp();                                      // every lane is done with this slot
         fill = slot;
         if (++slot == SPB_WSTAGES) { slot = 0; phase ^= 1u; }
     }
-    if (cur_seg >= 0) flush(prev_t);
     if constexpr (PACKED) pacc.store(acc);
     if constexpr (MODE == MODE_GRAD) gacc.store(acc);
     __syncthreads();
