@@ -160,6 +160,15 @@ int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t*
                       int64_t work_stride, float* out_pair, float* out_seg, void* ev_before,
                       void* ev_after, void* stream);
 
+/* One complete GN/LM iteration for n_pairs problems in TWO launches: spb_gn_accumulate's fused kernel, then one
+ * kernel that reduces the partials (into gn_pair / gn_seg), solves the damped system and retracts (what
+ * spb_gn_accumulate + spb_lm_update do in three).  Arguments as in those two functions. */
+int spb_gn_iterate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, const int32_t* seg_cnt,
+                   int n_pairs, int max_tiles, float irls_eps, int with_affine, float* work,
+                   int64_t work_stride, float* gn_pair, float* gn_seg, float* poses, float* k, float* aff_trg,
+                   float* lm_state, float* saved_pair, float* saved_seg, void* ev_before, void* ev_after,
+                   void* stream);
+
 /* Gradient mode over the same device-resident descriptors (batched Adam-parity iterations):
  * out_pair [n_pairs][SPB_PAIR_NOUT], out_gk [seg_total] (indexed seg_off[pair] + b). */
 int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off,

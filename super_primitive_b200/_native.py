@@ -63,6 +63,8 @@ _PROTOS = {
     "spb_workspace_floats_points": (_i64, [_i]),
     "spb_gn_ctas": (_i, [_i, _i]),
     "spb_gn_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "spb_gn_iterate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                            _vp, _vp]),
     "spb_grad_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "spb_lm_saved_floats": (_i, [_i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
     "spb_lm_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

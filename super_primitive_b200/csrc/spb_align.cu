@@ -359,6 +359,7 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
 
 #include "spb_fast.cuh"
 #include "spb_gn_packed.cuh"
+#include "spb_lm.cuh"
 
 #ifndef SPB_UNROLL
 #define SPB_UNROLL 1                           // unroll factor of the per-lane point loop
@@ -569,9 +570,10 @@ __global__ void k_finalize_grad(const __grid_constant__ SpbGeom g, int ctas, int
 }
 
 template <int NP>
-__global__ void k_finalize_gn(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
-                              const int32_t* __restrict__ seg_off, int ctas, const float* __restrict__ work,
-                              int64_t work_stride, float* __restrict__ out_pair, float* __restrict__ out_seg) {
+__device__ __forceinline__ void finalize_gn_body(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
+                                                 const int32_t* __restrict__ seg_off, int ctas,
+                                                 const float* __restrict__ work, int64_t work_stride,
+                                                 float* __restrict__ out_pair, float* __restrict__ out_seg) {
     constexpr int NACC = Sizes<MODE_GN, NP>::NACC;
     constexpr int NSEG = Sizes<MODE_GN, NP>::NSEG;
     constexpr int NA = NP * (NP + 1) / 2;
@@ -643,6 +645,28 @@ __global__ void k_finalize_gn(const SpbGeom* __restrict__ geoms, const SpbPair* 
             }
         }
     }
+}
+
+template <int NP>
+__global__ void k_finalize_gn(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
+                              const int32_t* __restrict__ seg_off, int ctas, const float* __restrict__ work,
+                              int64_t work_stride, float* __restrict__ out_pair, float* __restrict__ out_seg) {
+    finalize_gn_body<NP>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
+}
+
+// finalize + damped solve + retraction in ONE launch (one CTA per problem): the second kernel of a GN iteration
+template <int NP>
+__global__ void __launch_bounds__(256)
+k_gn_finalize_solve(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
+                    const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_cnt, int ctas,
+                    const float* __restrict__ work, int64_t work_stride, float* gn_pair, float* gn_seg,
+                    int with_affine, float* __restrict__ poses, float* __restrict__ k,
+                    float* __restrict__ aff_trg, float* __restrict__ lm_state, float* __restrict__ saved_pair,
+                    float* __restrict__ saved_seg) {
+    finalize_gn_body<NP>(geoms, pairs, seg_off, ctas, work, work_stride, gn_pair, gn_seg);
+    __threadfence_block();
+    __syncthreads();
+    lm_update_body(gn_pair, gn_seg, seg_off, seg_cnt, with_affine, poses, k, aff_trg, lm_state, saved_pair, saved_seg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -773,24 +797,13 @@ extern "C" int spb_cost_grad_points(const float* src_pts, const float* src_px, c
 
 extern "C" int spb_gn_ctas(int max_tiles, int n_pairs) { return ctas_for(max_tiles, n_pairs); }
 
-extern "C" int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, int n_pairs,
-                                 int max_tiles, float irls_eps, int with_affine, float* work, int64_t work_stride,
-                                 float* out_pair, float* out_seg, void* ev_before, void* ev_after, void* stream) {
-    if (!geoms || !pairs || !seg_off || n_pairs < 1 || max_tiles < 1 || !work || !out_pair || !out_seg)
-        return SPB_EINVAL;
-    if (n_pairs > 65535) return SPB_ELIMIT;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int ctas = ctas_for(max_tiles, n_pairs);
+static int launch_gn_align(const SpbGeom* geoms, const SpbPair* pairs, int n_pairs, int ctas, float irls_eps,
+                           int with_affine, float* work, int64_t work_stride, cudaStream_t st) {
     // with_affine: 0 = no brightness terms, 1 = optimise the target affine (8 pose columns),
     //              2 = brightness terms present but fixed (6 pose columns)
-    const bool np8 = with_affine == 1;
-    const int nacc = np8 ? Sizes<MODE_GN, 8>::NACC : Sizes<MODE_GN, 6>::NACC;
-    const int nseg = np8 ? Sizes<MODE_GN, 8>::NSEG : Sizes<MODE_GN, 6>::NSEG;
-    if (work_stride < (int64_t)ctas * nacc + (int64_t)max_tiles * nseg) return SPB_EINVAL;
     dim3 grid(ctas, n_pairs);
-    if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
     cudaError_t e;
-    if (np8) {
+    if (with_affine == 1) {
         if ((e = allow_dyn_smem(k_align_global<MODE_GN, 8, true>)) != cudaSuccess) return (int)e;
         k_align_global<MODE_GN, 8, true><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, irls_eps, work, work_stride);
     } else if (with_affine == 2) {
@@ -801,11 +814,64 @@ extern "C" int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, con
         k_align_global<MODE_GN, 6, false><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, irls_eps, work, work_stride);
     }
     SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+static bool gn_stride_ok(int ctas, int max_tiles, int with_affine, int64_t work_stride) {
+    const bool np8 = with_affine == 1;
+    const int nacc = np8 ? Sizes<MODE_GN, 8>::NACC : Sizes<MODE_GN, 6>::NACC;
+    const int nseg = np8 ? Sizes<MODE_GN, 8>::NSEG : Sizes<MODE_GN, 6>::NSEG;
+    return work_stride >= (int64_t)ctas * nacc + (int64_t)max_tiles * nseg;
+}
+
+extern "C" int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, int n_pairs,
+                                 int max_tiles, float irls_eps, int with_affine, float* work, int64_t work_stride,
+                                 float* out_pair, float* out_seg, void* ev_before, void* ev_after, void* stream) {
+    if (!geoms || !pairs || !seg_off || n_pairs < 1 || max_tiles < 1 || !work || !out_pair || !out_seg)
+        return SPB_EINVAL;
+    if (n_pairs > 65535) return SPB_ELIMIT;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = ctas_for(max_tiles, n_pairs);
+    if (!gn_stride_ok(ctas, max_tiles, with_affine, work_stride)) return SPB_EINVAL;
+    if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
+    const int rc = launch_gn_align(geoms, pairs, n_pairs, ctas, irls_eps, with_affine, work, work_stride, st);
+    if (rc != SPB_OK) return rc;
     if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
-    if (np8)
+    if (with_affine == 1)
         k_finalize_gn<8><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
     else
         k_finalize_gn<6><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_seg);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+// One complete GN/LM iteration in two launches: fused residual+Jacobian+normal-equation kernel, then
+// finalize + damped solve + retraction (k_gn_finalize_solve).
+extern "C" int spb_gn_iterate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, const int32_t* seg_cnt,
+                              int n_pairs, int max_tiles, float irls_eps, int with_affine, float* work,
+                              int64_t work_stride, float* gn_pair, float* gn_seg, float* poses, float* k,
+                              float* aff_trg, float* lm_state, float* saved_pair, float* saved_seg, void* ev_before,
+                              void* ev_after, void* stream) {
+    if (!geoms || !pairs || !seg_off || !seg_cnt || n_pairs < 1 || max_tiles < 1 || !work || !gn_pair || !gn_seg ||
+        !poses || !k || !lm_state || !saved_pair || !saved_seg)
+        return SPB_EINVAL;
+    if (n_pairs > 65535) return SPB_ELIMIT;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = ctas_for(max_tiles, n_pairs);
+    if (!gn_stride_ok(ctas, max_tiles, with_affine, work_stride)) return SPB_EINVAL;
+    if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
+    const int rc = launch_gn_align(geoms, pairs, n_pairs, ctas, irls_eps, with_affine, work, work_stride, st);
+    if (rc != SPB_OK) return rc;
+    if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
+    const int opt_aff = with_affine == 1 ? 1 : 0;
+    if (with_affine == 1)
+        k_gn_finalize_solve<8><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, seg_cnt, ctas, work, work_stride, gn_pair,
+                                                        gn_seg, opt_aff, poses, k, aff_trg, lm_state, saved_pair,
+                                                        saved_seg);
+    else
+        k_gn_finalize_solve<6><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, seg_cnt, ctas, work, work_stride, gn_pair,
+                                                        gn_seg, opt_aff, poses, k, aff_trg, lm_state, saved_pair,
+                                                        saved_seg);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

@@ -8,199 +8,14 @@
 //     [A   B ] [xi]      [g_p]
 //     [B^T D ] [dk] = -  [g_d]        D diagonal
 // LM: A <- A + lam diag(A), D <- D (1 + lam); Schur: S = A - B D^-1 B^T, solved in float64.
-#include "spb_common.cuh"
-
-#define SV_PAIR 80   // floats saved per problem : pose[16] aff[2] pad[14] gn_pair[48]
-#define SV_SEG 12    // floats saved per segment : k, pad, gn_seg[10]
-
-__device__ __forceinline__ int tri8(int r, int c) { return r * 8 - r * (r - 1) / 2 + (c - r); }
-
-__device__ void se3_exp_d(const double* xi, double* T /*3x4 row-major R|t*/) {
-    const double tx = xi[0], ty = xi[1], tz = xi[2], px = xi[3], py = xi[4], pz = xi[5];
-    const double th2 = px * px + py * py + pz * pz;
-    double A, B, C;
-    if (th2 < 1e-16) {
-        A = 1.0 - th2 / 6.0; B = 0.5 - th2 / 24.0; C = 1.0 / 6.0 - th2 / 120.0;
-    } else {
-        const double th = sqrt(th2);
-        A = sin(th) / th; B = (1.0 - cos(th)) / th2; C = (th - sin(th)) / (th2 * th);
-    }
-    const double K[9] = {0, -pz, py, pz, 0, -px, -py, px, 0};
-    double K2[9];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) K2[3 * i + j] = K[3 * i] * K[j] + K[3 * i + 1] * K[3 + j] + K[3 * i + 2] * K[6 + j];
-    const double tau[3] = {tx, ty, tz};
-    for (int i = 0; i < 3; ++i) {
-        double vt = 0.0;
-        for (int j = 0; j < 3; ++j) {
-            const double I = (i == j) ? 1.0 : 0.0;
-            T[4 * i + j] = I + A * K[3 * i + j] + B * K2[3 * i + j];
-            vt += (I + B * K[3 * i + j] + C * K2[3 * i + j]) * tau[j];
-        }
-        T[4 * i + 3] = vt;
-    }
-}
+#include "spb_lm.cuh"
 
 __global__ void __launch_bounds__(128)
 k_lm_update(const float* __restrict__ gn_pair, const float* __restrict__ gn_seg, const int32_t* __restrict__ seg_off,
             const int32_t* __restrict__ seg_cnt, int with_affine, float* __restrict__ poses, float* __restrict__ k,
             float* __restrict__ aff_trg, float* __restrict__ lm_state, float* __restrict__ saved_pair,
             float* __restrict__ saved_seg) {
-    const int p = blockIdx.x;
-    const int so = seg_off[p], n = seg_cnt[p];
-    float* st = lm_state + (size_t)p * SPB_LM_NSTATE;
-    float* sp = saved_pair + (size_t)p * SV_PAIR;
-    float* ss = saved_seg + (size_t)so * SV_SEG;
-    const float* gp = gn_pair + (size_t)p * SPB_GN_PAIR_NOUT;
-    const float* gs = gn_seg + (size_t)so * SPB_GN_SEG_NOUT;
-    float* pose = poses + (size_t)p * 16;
-    __shared__ int s_accept;
-    __shared__ float s_lam;
-    __shared__ double s_red[4][44];
-    __shared__ double s_xi[8];
-
-    if (threadIdx.x == 0) {
-        const float cost = gp[SPB_GN_NA + 8];
-        const bool init = st[2] != 0.f;
-        const bool acc = !init || (cost < st[1]);
-        float lam = st[0];
-        if (acc) {
-            st[1] = cost;
-            if (init) { lam = fmaxf(lam * 0.25f, 1e-7f); st[3] += 1.f; }
-            st[2] = 1.f;
-        } else {
-            lam = fminf(lam * 8.0f, 1e7f);
-            st[4] += 1.f;
-        }
-        st[0] = lam;
-        st[5] = cost;
-        s_accept = acc ? 1 : 0;
-        s_lam = lam;
-    }
-    __syncthreads();
-    const bool acc = s_accept != 0;
-    const double lam = (double)s_lam;
-    // accept: snapshot the current parameters and system; reject: roll the parameters back
-    if (acc) {
-        for (int i = threadIdx.x; i < 16; i += blockDim.x) sp[i] = pose[i];
-        if (threadIdx.x < 2) sp[16 + threadIdx.x] = (with_affine && aff_trg) ? aff_trg[2 * p + threadIdx.x] : 0.f;
-        for (int i = threadIdx.x; i < SPB_GN_PAIR_NOUT; i += blockDim.x) sp[32 + i] = gp[i];
-        for (int b = threadIdx.x; b < n; b += blockDim.x) {
-            ss[(size_t)b * SV_SEG] = k[so + b];
-            for (int i = 0; i < SPB_GN_SEG_NOUT; ++i) ss[(size_t)b * SV_SEG + 2 + i] = gs[(size_t)b * SPB_GN_SEG_NOUT + i];
-        }
-    }
-    __syncthreads();
-    const float* A = sp + 32;          // saved system (== current one after an accept)
-    // Schur complement accumulation over segments (float64)
-    double loc[44];
-#pragma unroll
-    for (int i = 0; i < 44; ++i) loc[i] = 0.0;
-    for (int b = threadIdx.x; b < n; b += blockDim.x) {
-        const float* sb = ss + (size_t)b * SV_SEG + 2;
-        const double D = (double)sb[8] * (1.0 + lam);
-        if (!(D > 1e-30)) continue;
-        const double inv = 1.0 / D;
-        const double gd = sb[9];
-        int q = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const double bi = (double)sb[i] * inv;
-#pragma unroll
-            for (int j = i; j < 8; ++j) loc[q++] += bi * (double)sb[j];
-            loc[36 + i] += bi * gd;
-        }
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < 44; ++i) {
-        double v = loc[i];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[warp][i] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double S[8][8], rhs[8];
-        for (int i = 0; i < 8; ++i) {
-            for (int j = i; j < 8; ++j) {
-                const int q = tri8(i, j);
-                double v = (double)A[q] - (s_red[0][q] + s_red[1][q] + s_red[2][q] + s_red[3][q]);
-                if (i == j) v += lam * (double)A[q];
-                S[i][j] = v; S[j][i] = v;
-            }
-            rhs[i] = -((double)A[SPB_GN_NA + i] - (s_red[0][36 + i] + s_red[1][36 + i] + s_red[2][36 + i] + s_red[3][36 + i]));
-        }
-        const int np = with_affine ? 8 : 6;
-        bool active[8];
-        for (int i = 0; i < 8; ++i) {
-            active[i] = (i < np) && (S[i][i] > 1e-30) && isfinite(S[i][i]);
-            if (!active[i]) {
-                for (int j = 0; j < 8; ++j) { S[i][j] = 0.0; S[j][i] = 0.0; }
-                S[i][i] = 1.0; rhs[i] = 0.0;
-            }
-        }
-        // Cholesky S = L L^T (in place, lower), tiny jitter for semi-definite cases
-        bool ok = true;
-        for (int j = 0; j < 8 && ok; ++j) {
-            double d = S[j][j];
-            for (int q = 0; q < j; ++q) d -= S[j][q] * S[j][q];
-            if (!(d > 0.0)) { ok = false; break; }
-            const double l = sqrt(d);
-            S[j][j] = l;
-            for (int i = j + 1; i < 8; ++i) {
-                double v = S[i][j];
-                for (int q = 0; q < j; ++q) v -= S[i][q] * S[j][q];
-                S[i][j] = v / l;
-            }
-        }
-        double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (ok) {
-            double y[8];
-            for (int i = 0; i < 8; ++i) {
-                double v = rhs[i];
-                for (int q = 0; q < i; ++q) v -= S[i][q] * y[q];
-                y[i] = v / S[i][i];
-            }
-            for (int i = 7; i >= 0; --i) {
-                double v = y[i];
-                for (int q = i + 1; q < 8; ++q) v -= S[q][i] * x[q];
-                x[i] = v / S[i][i];
-            }
-        } else {
-            st[0] = fminf(st[0] * 8.0f, 1e7f);   // not positive definite: damp harder next time
-        }
-        double nrm = 0.0;
-        for (int i = 0; i < 8; ++i) { s_xi[i] = x[i]; nrm += x[i] * x[i]; }
-        st[6] = (float)sqrt(nrm);
-        // T <- Exp(xi) T_saved
-        double E[12];
-        se3_exp_d(x, E);
-        for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 4; ++j) {
-                double v = E[4 * i] * (double)sp[j] + E[4 * i + 1] * (double)sp[4 + j] + E[4 * i + 2] * (double)sp[8 + j];
-                if (j == 3) v += E[4 * i + 3];
-                pose[4 * i + j] = (float)v;
-            }
-        }
-        pose[12] = 0.f; pose[13] = 0.f; pose[14] = 0.f; pose[15] = 1.f;
-        if (with_affine && aff_trg) {
-            aff_trg[2 * p] = sp[16] + (float)x[6];
-            aff_trg[2 * p + 1] = sp[17] + (float)x[7];
-        }
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < n; b += blockDim.x) {
-        const float* sb = ss + (size_t)b * SV_SEG + 2;
-        const double D = (double)sb[8] * (1.0 + lam);
-        double dk = 0.0;
-        if (D > 1e-30) {
-            double v = sb[9];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v += (double)sb[i] * s_xi[i];
-            dk = -v / D;
-        }
-        k[so + b] = ss[(size_t)b * SV_SEG] + (float)dk;
-    }
+    lm_update_body(gn_pair, gn_seg, seg_off, seg_cnt, with_affine, poses, k, aff_trg, lm_state, saved_pair, saved_seg);
 }
 
 extern "C" int spb_lm_saved_floats(int n_pairs, int seg_total, int64_t* pair_floats, int64_t* seg_floats) {

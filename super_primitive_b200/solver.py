@@ -144,10 +144,18 @@ class AlignmentBatch:
         self.launches += 1
 
     def gn_step(self, ev=None):
-        """One GN/LM iteration for every problem: fused residual+Jacobian+normal-equation kernel,
-        finalize, damped solve + retraction."""
-        self.gn_accumulate(ev)
-        self.lm_update()
+        """One GN/LM iteration for every problem in two launches: the fused residual+Jacobian+normal-equation
+        kernel, then finalize + damped solve + retraction (``spb_gn_iterate``)."""
+        e0, e1 = (None, None) if ev is None else (ev[0].cuda_event, ev[1].cuda_event)
+        nat.check(nat.lib().spb_gn_iterate(self.d_geoms.data_ptr(), self.d_pairs.data_ptr(), self.d_seg_off.data_ptr(),
+                                           self.d_seg_cnt.data_ptr(), self.n, self.max_tiles, self.irls_eps,
+                                           1 if self.with_affine else (2 if self.use_affine else 0),
+                                           self.work.data_ptr(), self.work_stride, self.gn_pair.data_ptr(),
+                                           self.gn_seg.data_ptr(), self.poses.data_ptr(), self.k.data_ptr(),
+                                           self.aff_trg.data_ptr() if self.with_affine else None,
+                                           self.lm_state.data_ptr(), self.saved_pair.data_ptr(),
+                                           self.saved_seg.data_ptr(), e0, e1, _stream()), "spb_gn_iterate")
+        self.launches += 2
 
     def grad_step(self, ev=None):
         """Cost + first-order gradient for every problem (Adam-parity quantities): fills
