@@ -212,6 +212,10 @@ int spb_depth_splat(const SpbGeom* geom, const float* k, const float* pose /* NU
 int spb_depth_splat_points(const float* pts, int P, const float* K, int H, int W, int mean,
                            unsigned long long* keys, float* sum, float* out, uint8_t* valid, void* stream);
 
+/* One image-pyramid step (image/gaussian_pyramid.py:53-85): dst (C, ceil(H/2), ceil(W/2)) = 3x3 [1 2 1]^2/16 blur
+ * with reflect padding of src (C,H,W), decimated [::2, ::2]. */
+int spb_pyr_down(const float* src, int C, int H, int W, float* dst, void* stream);
+
 /* lifted points of a keyframe: src_pts [n][3] (core/dense_optim.py:176-200) */
 int spb_lift_points(const SpbGeom* geom, const float* k, float* src_pts, int64_t* seg_ids,
                     uint8_t* src_ok, void* stream);

@@ -37,3 +37,13 @@ def install_depth_init():
     mod = importlib.import_module(f"{__name__}.depth_init")
     sys.modules["odometery.depth_init"] = mod
     return mod
+
+
+def install_pyramid():
+    """Replace ``image.keyframe.keyframe_pyramid`` of the (already importable) reference with the CUDA pyramid;
+    callers use ``keyframe.keyframe_pyramid(...)`` through the module attribute, so patching it is enough."""
+    import importlib
+    ref_mod = importlib.import_module("image.keyframe")
+    mod = importlib.import_module(f"{__name__}.pyramid")
+    ref_mod.keyframe_pyramid = mod.keyframe_pyramid
+    return mod

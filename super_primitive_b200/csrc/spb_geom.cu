@@ -367,6 +367,50 @@ extern "C" int spb_depth_splat(const SpbGeom* geom, const float* k, const float*
     return SPB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// image pyramid level: 3x3 [1 2 1]^2/16 Gaussian with reflect padding, then [::2, ::2]
+// (image/gaussian_pyramid.py:53-85); one thread per output pixel per channel, rows coalesced
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pyr_down(const float* __restrict__ src, int C, int H, int W, float* __restrict__ dst, int Ho,
+                           int Wo) {
+    const int c = blockIdx.z;
+    const int yo = blockIdx.y;
+    const float* s = src + (size_t)c * H * W;
+    float* d = dst + ((size_t)c * Ho + yo) * Wo;
+    const int y = 2 * yo;
+    const int ym = (y == 0) ? (H > 1 ? 1 : 0) : y - 1;                     // reflect: -1 -> 1
+    const int yp = (y + 1 >= H) ? (H > 1 ? H - 2 : 0) : y + 1;             // reflect:  H -> H-2
+    const float* r0 = s + (size_t)ym * W;
+    const float* r1 = s + (size_t)y * W;
+    const float* r2 = s + (size_t)yp * W;
+    for (int xo = blockIdx.x * blockDim.x + threadIdx.x; xo < Wo; xo += gridDim.x * blockDim.x) {
+        const int x = 2 * xo;
+        const int xm = (x == 0) ? (W > 1 ? 1 : 0) : x - 1;
+        const int xp = (x + 1 >= W) ? (W > 1 ? W - 2 : 0) : x + 1;
+        // same association as a 3x3 convolution accumulated row-major: weights w/16
+        float acc = 0.0625f * r0[xm];
+        acc = fmaf(0.125f, r0[x], acc);
+        acc = fmaf(0.0625f, r0[xp], acc);
+        acc = fmaf(0.125f, r1[xm], acc);
+        acc = fmaf(0.25f, r1[x], acc);
+        acc = fmaf(0.125f, r1[xp], acc);
+        acc = fmaf(0.0625f, r2[xm], acc);
+        acc = fmaf(0.125f, r2[x], acc);
+        acc = fmaf(0.0625f, r2[xp], acc);
+        d[xo] = acc;
+    }
+}
+
+extern "C" int spb_pyr_down(const float* src, int C, int H, int W, float* dst, void* stream) {
+    if (!src || !dst || C < 1 || C > 65535 || H < 1 || W < 1) return SPB_EINVAL;
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    if (Ho > 65535) return SPB_ELIMIT;
+    dim3 grid((Wo + 127) / 128, Ho, C);
+    k_pyr_down<<<grid, 128, 0, (cudaStream_t)stream>>>(src, C, H, W, dst, Ho, Wo);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
 // estimate_depth_diff for arbitrary points (core/ops.py:59-96): same splat as k_lift<true>, input (P,3)
 __global__ void k_splat_points(const float* __restrict__ pts, int P, const float* __restrict__ K, int H, int W,
                                int mean, unsigned long long* __restrict__ keys, float* __restrict__ sum,

@@ -276,7 +276,37 @@ def main():
     # 3-level pyramid at a reduced C2-like shape
     case_full("pyr3_rects", 96, 128, 12, "rects", 0.01, (0, 3), 2, True, seed=11, stats=False)
     case_adam("adam_c1", 96, 128, 8, "overlap", 40, seed=13)
+    case_pyramid("pyramid_odd", 45, 70, 4, seed=17)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--pyramid-only" not in sys.argv:
     main()
+
+
+def case_pyramid(name, H, W, N, seed):
+    """The reference's own keyframe_pyramid (image/keyframe.py:77-148, geo_down=False) on a synthetic keyframe,
+    incl. odd sizes: pins the blur/decimate and K_img semantics used by synthetic.keyframe_pyramid and by the
+    CUDA pyramid kernel."""
+    from image.keyframe import keyframe_pyramid as ref_pyr
+    kf = syn.make_keyframe(H, W, N, kind="rects", seed=seed, noise=0.02)
+    store = dict(H=H, W=W, image=t2n(kf.image), K=t2n(kf.K))
+    for (a, b) in [(0, 3), (1, 4), (0, 1)]:
+        levels = ref_pyr(ref_kf(kf), a, b)
+        torch.set_grad_enabled(True)
+        mine = syn.keyframe_pyramid(kf, a, b)
+        assert len(levels) == len(mine)
+        for i, (r, m) in enumerate(zip(levels, mine)):
+            same(r.image, m.image, f"{name}/pyr{a}{b}/L{i}/image")
+            same(r.K_img, m.K_img, f"{name}/pyr{a}{b}/L{i}/K_img")
+            same(r.K, m.K, f"{name}/pyr{a}{b}/L{i}/K")
+            assert r.logdepth_perseg is kf.logdepth_perseg or torch.equal(r.logdepth_perseg, kf.logdepth_perseg)
+            store[f"p{a}{b}_L{i}_image"] = t2n(r.image)
+            store[f"p{a}{b}_L{i}_K_img"] = t2n(r.K_img)
+        store[f"p{a}{b}_n"] = len(levels)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **store)
+    print(f"{name}: wrote {os.path.getsize(path) / 1e3:.0f} kB")
+
+
+if __name__ == "__main__" and "--pyramid-only" in sys.argv:
+    case_pyramid("pyramid_odd", 45, 70, 4, seed=17)

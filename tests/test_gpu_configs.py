@@ -161,3 +161,24 @@ def test_estimate_depth_diff_points_against_oracle():
         assert (to_np(valid) != to_np(ref_valid)).mean() < 1e-3
         bad = np.abs(to_np(img) - to_np(ref_img)) > 1e-4 * np.maximum(np.abs(to_np(ref_img)), 1e-3)
         assert bad.mean() < 2e-3, f"mean={mean}: {bad.sum()} differing pixels"
+
+
+def test_keyframe_pyramid_matches_reference():
+    """image/keyframe.py:77-148 (geo_down=False): the CUDA blur/decimate against the reference's own pyramid
+    frozen in tests/golden/pyramid_odd.npz (odd sizes 45x70)."""
+    import os
+    from tests.common import GOLDEN_DIR
+    from super_primitive_b200.keyframe import KeyFrame
+    from super_primitive_b200.pyramid import keyframe_pyramid
+    z = np.load(os.path.join(GOLDEN_DIR, "pyramid_odd.npz"))
+    kf = KeyFrame(torch.from_numpy(z["image"]).cuda(), torch.from_numpy(z["K"]).cuda())
+    for a, b in [(0, 3), (1, 4), (0, 1)]:
+        levels = keyframe_pyramid(kf, a, b)
+        assert torch.is_grad_enabled()
+        assert len(levels) == int(z[f"p{a}{b}_n"])
+        for i, lv in enumerate(levels):
+            ref = z[f"p{a}{b}_L{i}_image"]
+            assert tuple(lv.image.shape) == ref.shape
+            assert_close(to_np(lv.image), ref, 1e-6, f"pyramid {a}{b} level {i}")
+            assert_close(to_np(lv.K_img), z[f"p{a}{b}_L{i}_K_img"], 1e-7, "K_img")
+            assert lv.is_supporting()

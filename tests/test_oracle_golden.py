@@ -107,3 +107,20 @@ def test_closed_form_gn_blocks_are_consistent():
     assert_close(r["g_p"][:3] / P3, gp[:3, 3], 1e-9, "translation block")
     xi, dk = cf.lm_step(r["A"], r["B"], r["D"], r["g_p"], r["g_d"], 1e-3)
     assert np.all(np.isfinite(xi)) and np.all(np.isfinite(dk))
+
+
+def test_synthetic_pyramid_reproduces_reference_pyramid():
+    """synthetic.keyframe_pyramid (used to build every multi-level test input) against the reference's own
+    keyframe_pyramid outputs, odd image size."""
+    import os
+    from tests.common import GOLDEN_DIR
+    from super_primitive_b200 import synthetic as syn
+    from super_primitive_b200.keyframe import KeyFrame
+    z = np.load(os.path.join(GOLDEN_DIR, "pyramid_odd.npz"))
+    kf = KeyFrame(torch.from_numpy(z["image"]), torch.from_numpy(z["K"]))
+    for a, b in [(0, 3), (1, 4), (0, 1)]:
+        levels = syn.keyframe_pyramid(kf, a, b)
+        assert len(levels) == int(z[f"p{a}{b}_n"])
+        for i, lv in enumerate(levels):
+            assert_close(to_np(lv.image), z[f"p{a}{b}_L{i}_image"], 1e-6, "image")
+            assert_close(to_np(lv.K_img), z[f"p{a}{b}_L{i}_K_img"], 1e-7, "K_img")
