@@ -212,6 +212,16 @@ int spb_depth_splat(const SpbGeom* geom, const float* k, const float* pose /* NU
 int spb_depth_splat_points(const float* pts, int P, const float* K, int H, int W, int mean,
                            unsigned long long* keys, float* sum, float* out, uint8_t* valid, void* stream);
 
+/* VOID depth-completion tail (depth_completion/segment_based_completion.py:21-27): per-pixel average of the valid
+ * (>1e-6) entries of N stacked depth maps; entries <1e-6 are zeroed IN PLACE like the reference; invalid = no map
+ * has a depth >= 1e-6 at the pixel. */
+int spb_depth_avg_dense(float* depths, int N, int H, int W, float* out, uint8_t* invalid, void* stream);
+
+/* The same result straight from the compact geometry (lines 48-54 fused: unproject_kf_to_depths, mask, drop the
+ * segments with visible[b] == 0, average) without materialising (N,H,W); sum/cnt: [H*W] float scratch. */
+int spb_depth_avg_compact(const SpbGeom* geom, const float* k, const uint8_t* visible, float* sum, float* cnt,
+                          float* out, uint8_t* invalid, void* stream);
+
 /* One image-pyramid step (image/gaussian_pyramid.py:53-85): dst (C, ceil(H/2), ceil(W/2)) = 3x3 [1 2 1]^2/16 blur
  * with reflect padding of src (C,H,W), decimated [::2, ::2]. */
 int spb_pyr_down(const float* src, int C, int H, int W, float* dst, void* stream);

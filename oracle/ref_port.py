@@ -339,3 +339,21 @@ def segment_median_reinit(est_depth, kf, mode='median'):
     out[vis] += at_kp[vis]
     out[~vis] = torch.median(out[vis])
     return out, vis
+
+
+def average_render(depths):
+    """Per-pixel average of the valid entries of stacked depth maps; zeroes entries < 1e-6 in place.
+    depth_completion/segment_based_completion.py:21-27"""
+    invalid = depths.max(dim=0)[0] < 1e-6
+    depths[depths < 1e-6] = 0.0
+    n_valid = ((depths > 1e-6).sum(dim=0) + 1e-6)
+    return depths.sum(dim=0) / n_valid, invalid
+
+
+def completion_render(kf, k, visible):
+    """depth_completion/segment_based_completion.py:48-54: dense depths, -1 outside masks, drop unseeded
+    segments, average."""
+    d = dense_depths(kf, k)
+    d[kf.keypoint_regions == 0] = -1
+    d = d[visible]
+    return average_render(d)

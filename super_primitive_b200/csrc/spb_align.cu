@@ -715,14 +715,26 @@ __global__ void k_finalize_points(int ctas, int P, const float* __restrict__ wor
 // ------------------------------------------------------------------------------------------------
 // host-side launch helpers (C ABI)
 // ------------------------------------------------------------------------------------------------
-static inline int ctas_for(int n_tiles, int n_pairs) {
-    // every warp streams a strided set of tiles through its own ring; aim at ~4 waves of 3 CTAs/SM over
-    // all pairs so the tail wave is small, but keep >= 2 tiles per warp when there is enough work
+static inline int ctas_for(int n_tiles, int n_pairs, int occ) {
+    // every warp streams a strided set of tiles through its own ring.  Size the grid to a whole number of waves
+    // of the kernel's occupancy (`occ` CTAs/SM on 148 SMs): ~4 waves over all pairs, rounded DOWN so the last
+    // wave is nearly full (a 5.3-wave grid wastes a third of its last wave).
     const int max_ctas = (n_tiles + SPB_WARPS - 1) / SPB_WARPS;
-    int want = (148 * 4 * 4 + n_pairs - 1) / (n_pairs > 0 ? n_pairs : 1);
+    const int slots = 148 * occ;
+    if (n_pairs < 1) n_pairs = 1;
+    if ((long long)n_pairs * max_ctas <= slots) return max_ctas;
+    int want = (slots * 4) / n_pairs;
     if (want > max_ctas) want = max_ctas;
     if (want < 1) want = 1;
     return want;
+}
+static inline int ctas_grad(int n_tiles, int n_pairs) { return ctas_for(n_tiles, n_pairs, Occ<MODE_GRAD, 6>::CTAS); }
+static inline int ctas_gn(int n_tiles, int n_pairs, int with_affine) {
+    return ctas_for(n_tiles, n_pairs, with_affine == 1 ? Occ<MODE_GN, 8>::CTAS : Occ<MODE_GN, 6>::CTAS);
+}
+static inline int ctas_max(int n_tiles, int n_pairs) {
+    int a = ctas_grad(n_tiles, n_pairs), b = ctas_gn(n_tiles, n_pairs, 0), c = ctas_gn(n_tiles, n_pairs, 1);
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 template <typename K>
@@ -738,7 +750,7 @@ static inline int ctas_for_points(int P) {
 }
 
 extern "C" int64_t spb_workspace_floats(const SpbGeom* geom, int B, int gn) {
-    const int ctas = ctas_for(geom->n_tiles, B);
+    const int ctas = ctas_max(geom->n_tiles, B);
     const int nacc = gn ? Sizes<MODE_GN, 8>::NACC : SPB_PAIR_NOUT;
     const int nseg = gn ? Sizes<MODE_GN, 8>::NSEG : 1;
     return (int64_t)B * ((int64_t)ctas * nacc + (int64_t)geom->n_tiles * nseg);
@@ -759,7 +771,7 @@ extern "C" int spb_cost_grad(const SpbGeom* geom, const SpbPair* pairs, int B, f
     PairPack pack;
     for (int j = 0; j < B; ++j) pack.p[j] = pairs[j];
     for (int j = B; j < 16; ++j) pack.p[j] = pairs[0];
-    const int ctas = ctas_for(geom->n_tiles, B);
+    const int ctas = ctas_grad(geom->n_tiles, B);
     dim3 grid(ctas, B);
     if (stats) {
         k_align_stats<<<grid, SPB_THREADS, 0, st>>>(*geom, pack, work, *stats);
@@ -795,7 +807,7 @@ extern "C" int spb_cost_grad_points(const float* src_pts, const float* src_px, c
     return SPB_OK;
 }
 
-extern "C" int spb_gn_ctas(int max_tiles, int n_pairs) { return ctas_for(max_tiles, n_pairs); }
+extern "C" int spb_gn_ctas(int max_tiles, int n_pairs) { return ctas_max(max_tiles, n_pairs); }
 
 static int launch_gn_align(const SpbGeom* geoms, const SpbPair* pairs, int n_pairs, int ctas, float irls_eps,
                            int with_affine, float* work, int64_t work_stride, cudaStream_t st) {
@@ -831,7 +843,7 @@ extern "C" int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, con
         return SPB_EINVAL;
     if (n_pairs > 65535) return SPB_ELIMIT;
     cudaStream_t st = (cudaStream_t)stream;
-    const int ctas = ctas_for(max_tiles, n_pairs);
+    const int ctas = ctas_gn(max_tiles, n_pairs, with_affine);
     if (!gn_stride_ok(ctas, max_tiles, with_affine, work_stride)) return SPB_EINVAL;
     if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
     const int rc = launch_gn_align(geoms, pairs, n_pairs, ctas, irls_eps, with_affine, work, work_stride, st);
@@ -857,7 +869,7 @@ extern "C" int spb_gn_iterate(const SpbGeom* geoms, const SpbPair* pairs, const 
         return SPB_EINVAL;
     if (n_pairs > 65535) return SPB_ELIMIT;
     cudaStream_t st = (cudaStream_t)stream;
-    const int ctas = ctas_for(max_tiles, n_pairs);
+    const int ctas = ctas_gn(max_tiles, n_pairs, with_affine);
     if (!gn_stride_ok(ctas, max_tiles, with_affine, work_stride)) return SPB_EINVAL;
     if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
     const int rc = launch_gn_align(geoms, pairs, n_pairs, ctas, irls_eps, with_affine, work, work_stride, st);
@@ -909,7 +921,7 @@ extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, c
         return SPB_EINVAL;
     if (n_pairs > 65535) return SPB_ELIMIT;
     cudaStream_t st = (cudaStream_t)stream;
-    const int ctas = ctas_for(max_tiles, n_pairs);
+    const int ctas = ctas_grad(max_tiles, n_pairs);
     if (work_stride < (int64_t)ctas * SPB_PAIR_NOUT + max_tiles) return SPB_EINVAL;
     dim3 grid(ctas, n_pairs);
     if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);

@@ -411,6 +411,88 @@ extern "C" int spb_pyr_down(const float* src, int C, int H, int W, float* dst, v
     return SPB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// VOID depth completion tail (depth_completion/segment_based_completion.py:21-27,48-54)
+// ------------------------------------------------------------------------------------------------
+// dense drop-in of render_depth_avg: per pixel over the N stacked depth maps, in place like the reference
+__global__ void k_depth_avg_dense(float* __restrict__ depths, int N, int HW, float* __restrict__ out,
+                                  uint8_t* __restrict__ invalid) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        float mx = -INFINITY, sum = 0.f;
+        int cnt = 0;
+        for (int b = 0; b < N; ++b) {
+            float d = depths[(size_t)b * HW + i];
+            mx = fmaxf(mx, d);
+            if (d < 1e-6f) { d = 0.f; depths[(size_t)b * HW + i] = 0.f; }
+            sum += d;
+            cnt += d > 1e-6f;
+        }
+        out[i] = sum / ((float)cnt + 1e-6f);
+        invalid[i] = mx < 1e-6f;
+    }
+}
+
+// fused variant straight from the compact geometry: no (N,H,W) tensor is ever materialised
+__global__ void k_depth_avg_compact(const __grid_constant__ SpbGeom g, const float* __restrict__ k,
+                                    const uint8_t* __restrict__ visible, float* __restrict__ sum,
+                                    float* __restrict__ cnt) {
+    const int lane = threadIdx.x & 31;
+    const int wglobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int wstride = gridDim.x * (blockDim.x >> 5);
+    const int4* tiles = reinterpret_cast<const int4*>(g.tiles);
+    for (int t = wglobal; t < g.n_tiles; t += wstride) {
+        const int4 td = tiles[t];
+        if (visible != nullptr && !visible[td.x]) continue;
+        const float shift = k[td.x] - g.seg_lkp[td.x];
+        for (int i = lane; i < td.z; i += 32) {
+            const int p = td.y + i;
+            const uint32_t w = g.uv[p];
+            const int u = (int)(w & 0xffffu), v = (int)((w >> 16) & 0x7fffu);
+            const float z = expf(g.logd[p] + shift);
+            if (z > 1e-6f) {
+                atomicAdd(sum + (size_t)v * g.W + u, z);
+                atomicAdd(cnt + (size_t)v * g.W + u, 1.0f);
+            }
+        }
+    }
+}
+
+__global__ void k_depth_avg_resolve(const float* __restrict__ sum, const float* __restrict__ cnt, int HW,
+                                    float* __restrict__ out, uint8_t* __restrict__ invalid) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        out[i] = sum[i] / (cnt[i] + 1e-6f);
+        invalid[i] = cnt[i] == 0.f;
+    }
+}
+
+extern "C" int spb_depth_avg_dense(float* depths, int N, int H, int W, float* out, uint8_t* invalid, void* stream) {
+    if (!depths || !out || !invalid || N < 1 || H < 1 || W < 1) return SPB_EINVAL;
+    const int HW = H * W;
+    int bx = (HW + 255) / 256;
+    if (bx > 148 * 16) bx = 148 * 16;
+    k_depth_avg_dense<<<bx, 256, 0, (cudaStream_t)stream>>>(depths, N, HW, out, invalid);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+extern "C" int spb_depth_avg_compact(const SpbGeom* geom, const float* k, const uint8_t* visible, float* sum,
+                                     float* cnt, float* out, uint8_t* invalid, void* stream) {
+    if (!geom || !k || !sum || !cnt || !out || !invalid || geom->n_tiles < 1) return SPB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = geom->H * geom->W;
+    cudaError_t e = cudaMemsetAsync(sum, 0, sizeof(float) * (size_t)HW, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(cnt, 0, sizeof(float) * (size_t)HW, st);
+    if (e != cudaSuccess) return (int)e;
+    k_depth_avg_compact<<<lift_blocks(geom->n_tiles), 256, 0, st>>>(*geom, k, visible, sum, cnt);
+    SPB_CHECK_LAUNCH();
+    int bx = (HW + 255) / 256;
+    if (bx > 148 * 8) bx = 148 * 8;
+    k_depth_avg_resolve<<<bx, 256, 0, st>>>(sum, cnt, HW, out, invalid);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
 // estimate_depth_diff for arbitrary points (core/ops.py:59-96): same splat as k_lift<true>, input (P,3)
 __global__ void k_splat_points(const float* __restrict__ pts, int P, const float* __restrict__ K, int H, int W,
                                int mean, unsigned long long* __restrict__ keys, float* __restrict__ sum,

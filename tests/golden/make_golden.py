@@ -277,9 +277,10 @@ def main():
     case_full("pyr3_rects", 96, 128, 12, "rects", 0.01, (0, 3), 2, True, seed=11, stats=False)
     case_adam("adam_c1", 96, 128, 8, "overlap", 40, seed=13)
     case_pyramid("pyramid_odd", 45, 70, 4, seed=17)
+    case_completion("completion", 60, 80, 12, seed=19)
 
 
-if __name__ == "__main__" and "--pyramid-only" not in sys.argv:
+if __name__ == "__main__" and "--pyramid-only" not in sys.argv and "--completion-only" not in sys.argv:
     main()
 
 
@@ -308,5 +309,41 @@ def case_pyramid(name, H, W, N, seed):
     print(f"{name}: wrote {os.path.getsize(path) / 1e3:.0f} kB")
 
 
+def _reference_function(path, name, namespace):
+    """Compile ONE function of a reference module that cannot be imported here (its module imports SAM etc.) and
+    return it: the reference's own code runs, nothing is copied."""
+    import ast
+    tree = ast.parse(open(os.path.join(REF, path)).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name][0]
+    ns = dict(namespace)
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), os.path.join(REF, path), "exec"), ns)
+    return ns[name]
+
+
+def case_completion(name, H, W, N, seed):
+    """VOID depth-completion tail: the reference's render_depth_avg (depth_completion/segment_based_completion.py:21-27)
+    applied to unproject_kf_to_depths output with unseeded segments dropped (lines 48-54)."""
+    ref_avg = _reference_function("depth_completion/segment_based_completion.py", "render_depth_avg", {"torch": torch})
+    kf = syn.make_keyframe(H, W, N, kind="rects", seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    k = float(np.log(2.0)) + 0.2 * torch.randn(N, generator=g)
+    vis = torch.rand(N, generator=g) > 0.2
+    with torch.no_grad():
+        d = ref_do.unproject_kf_to_depths(ref_kf(kf), k)
+        d[kf.keypoint_regions == 0] = -1
+        d = d[vis]
+        avg_r, inv_r = ref_avg(d.clone())
+        avg_p, inv_p = port.completion_render(kf, k, vis)
+    same(avg_r, avg_p, f"{name}/avg")
+    same(inv_r, inv_p, f"{name}/invalid")
+    store = dict(H=H, W=W, N=N, k=t2n(k), visible=t2n(vis), avg=t2n(avg_r), invalid=t2n(inv_r))
+    store.update(inputs_dict(kf))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **store)
+    print(f"{name}: wrote {os.path.getsize(path) / 1e3:.0f} kB")
+
+
 if __name__ == "__main__" and "--pyramid-only" in sys.argv:
     case_pyramid("pyramid_odd", 45, 70, 4, seed=17)
+if __name__ == "__main__" and "--completion-only" in sys.argv:
+    case_completion("completion", 60, 80, 12, seed=19)

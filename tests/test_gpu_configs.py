@@ -182,3 +182,40 @@ def test_keyframe_pyramid_matches_reference():
             assert_close(to_np(lv.image), ref, 1e-6, f"pyramid {a}{b} level {i}")
             assert_close(to_np(lv.K_img), z[f"p{a}{b}_L{i}_K_img"], 1e-7, "K_img")
             assert lv.is_supporting()
+
+
+def test_depth_completion_average_render():
+    """BASELINE config 4 tail: render_depth_avg (dense, in place) and the fused compact variant vs the oracle."""
+    from oracle import ref_port as port
+    from super_primitive_b200 import synthetic as syn
+    from super_primitive_b200.depth_completion import render_depth_avg, render_segments_avg
+    kf = syn.make_keyframe(120, 160, 30, kind="rects", seed=8)
+    k = float(np.log(2.0)) + 0.2 * torch.randn(30, generator=torch.Generator().manual_seed(4))
+    vis = torch.ones(30, dtype=torch.bool)
+    vis[[3, 11, 12]] = False
+    with torch.no_grad():
+        ref_avg, ref_inv = port.completion_render(kf, k, vis)
+        dense = port.dense_depths(kf, k)
+        dense[kf.keypoint_regions == 0] = -1
+        dense = dense[vis].contiguous()
+    d_gpu = dense.clone().cuda()
+    avg, inv = render_depth_avg(d_gpu)
+    assert np.array_equal(to_np(inv), to_np(ref_inv))
+    assert_close(to_np(avg), to_np(ref_avg), 1e-6, "dense average")
+    assert float(d_gpu.min()) >= 0.0                      # negatives zeroed in place like the reference
+    avg2, inv2 = render_segments_avg(kf.to("cuda"), k.cuda(), vis.cuda())
+    assert np.array_equal(to_np(inv2), to_np(ref_inv))
+    assert_close(to_np(avg2), to_np(ref_avg), 1e-5, "compact average")
+
+
+def test_depth_completion_against_reference_golden():
+    import os
+    from tests.common import GOLDEN_DIR
+    from super_primitive_b200.depth_completion import render_segments_avg
+    from super_primitive_b200.keyframe import KeyFrame
+    z = np.load(os.path.join(GOLDEN_DIR, "completion.npz"))
+    t = lambda k: torch.from_numpy(z[k]).cuda()   # noqa: E731
+    kf = KeyFrame(t("src_image"), t("src_K"), t("src_logdepth"), t("src_keypoints"), t("src_regions"))
+    avg, inv = render_segments_avg(kf, t("k"), t("visible"))
+    assert np.array_equal(to_np(inv), z["invalid"])
+    assert_close(to_np(avg), z["avg"], 1e-5, "average render vs reference")

@@ -124,3 +124,17 @@ def test_synthetic_pyramid_reproduces_reference_pyramid():
         for i, lv in enumerate(levels):
             assert_close(to_np(lv.image), z[f"p{a}{b}_L{i}_image"], 1e-6, "image")
             assert_close(to_np(lv.K_img), z[f"p{a}{b}_L{i}_K_img"], 1e-7, "K_img")
+
+
+def test_completion_render_reproduces_reference():
+    """oracle.completion_render against the reference's render_depth_avg pipeline (completion.npz)."""
+    import os
+    from tests.common import GOLDEN_DIR
+    from super_primitive_b200.keyframe import KeyFrame
+    z = np.load(os.path.join(GOLDEN_DIR, "completion.npz"))
+    t = lambda k: torch.from_numpy(z[k])   # noqa: E731
+    kf = KeyFrame(t("src_image"), t("src_K"), t("src_logdepth"), t("src_keypoints"), t("src_regions"))
+    with torch.no_grad():
+        avg, inv = port.completion_render(kf, t("k"), t("visible"))
+    assert np.array_equal(to_np(inv), z["invalid"])
+    assert_close(to_np(avg), z["avg"], 1e-6, "average render")
