@@ -481,10 +481,10 @@ struct PairPack {
 // occupancy target: 3 CTAs/SM (<= 80 registers) for the gradient kernel, 2 for the GN kernel whose
 // 38 accumulators do not fit 80 registers without spilling
 #ifndef SPB_OCC_GRAD
-#define SPB_OCC_GRAD (SPB_PIPE == 2 ? 2 : 4)
+#define SPB_OCC_GRAD 4                          // CTAs/SM the gradient kernel is compiled for (64 registers)
 #endif
 #ifndef SPB_OCC_GN
-#define SPB_OCC_GN (SPB_PIPE == 2 ? 2 : 3)
+#define SPB_OCC_GN 3                            // 6-column GN kernel: 80 registers
 #endif
 template <int MODE, int NP>
 struct Occ {   // the 8-column (affine) GN variant keeps 47 accumulators: 2 CTAs/SM, no spills

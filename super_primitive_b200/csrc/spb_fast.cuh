@@ -18,9 +18,6 @@
 #pragma once
 #include "spb_common.cuh"
 
-#ifndef SPB_PIPE
-#define SPB_PIPE 1                             // points per lane whose taps are in flight (1 or 2)
-#endif
 #ifndef SPB_WSTAGES
 #define SPB_WSTAGES 2                          // ring slots per warp
 #endif
@@ -157,46 +154,8 @@ __device__ __forceinline__ void load_taps(const float4* __restrict__ trg, int Wl
     t.nw = __ldg(p0); t.ne = __ldg(p0 + 1); t.sw = __ldg(p0 + Wl); t.se = __ldg(p0 + Wl + 1);
 }
 
-// ---- gradient mode --------------------------------------------------------------------------------
-// acc[16] = cost, gt[3], gM[9] (d cost / d M; the finalize kernel scales columns by 1/fx, 1/fy to get
-//           d cost / d R), ga, gb, nvalid ; gk = d cost / d k of the tile's segment
-template <bool AFF>
-__device__ __forceinline__ void point_grad(const float* __restrict__ c, const Taps4& tp,
-                                           const Proj& q, float Is0, float Is1, float Is2,
-                                           float (&acc)[16], float& gk) {
-    const float4 nw = tp.nw, ne = tp.ne, sw = tp.sw, se = tp.se;
-    float I[3], dx[3], dy[3];
-    blend(nw.x, ne.x, sw.x, se.x, q.fx, q.fy, I[0], dx[0], dy[0]);
-    blend(nw.y, ne.y, sw.y, se.y, q.fx, q.fy, I[1], dx[1], dy[1]);
-    blend(nw.z, ne.z, sw.z, se.z, q.fx, q.fy, I[2], dx[2], dy[2]);
-    const float Is[3] = {Is0, Is1, Is2};
-    float gx = 0.f, gy = 0.f, ga = 0.f, gb = 0.f, cost = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const float r = AFF ? (Is[ch] - fmaf(c[F_EA], I[ch], c[F_BB])) : (Is[ch] - I[ch]);
-        cost += fabsf(r);
-        const float s = (r > 0.f) ? 1.0f : ((r < 0.f) ? -1.0f : 0.0f);
-        gx = fmaf(s, dx[ch], gx);
-        gy = fmaf(s, dy[ch], gy);
-        if (AFF) { ga = fmaf(s, I[ch], ga); gb += s; }
-    }
-    const float gxb = c[F_CU] * gx, gyb = c[F_CV] * gy;            // d cost / d (x_, y_)
-    const float gYx = gxb * q.rho, gYy = gyb * q.rho;
-    const float gYz = q.live ? -fmaf(gYx, q.xb, gYy * q.yb) : 0.0f;
-    const float zu = q.zs * q.uc, zv = q.zs * q.vc;
-    acc[0] += cost;
-    acc[1] += gYx; acc[2] += gYy; acc[3] += gYz;
-    acc[4] = fmaf(gYx, zu, acc[4]);   acc[5] = fmaf(gYx, zv, acc[5]);   acc[6] = fmaf(gYx, q.zs, acc[6]);
-    acc[7] = fmaf(gYy, zu, acc[7]);   acc[8] = fmaf(gYy, zv, acc[8]);   acc[9] = fmaf(gYy, q.zs, acc[9]);
-    acc[10] = fmaf(gYz, zu, acc[10]); acc[11] = fmaf(gYz, zv, acc[11]); acc[12] = fmaf(gYz, q.zs, acc[12]);
-    if (AFF) { acc[13] = fmaf(c[F_EA], ga, acc[13]); acc[14] -= gb; }
-    acc[15] += 1.0f;
-    // d cost / d k_b = gY . (R X) = gY . Y - gY . t, and gY . Y == 0 when the reciprocal is live
-    gk -= fmaf(gYx, c[F_TR(0)], fmaf(gYy, c[F_TR(1)], gYz * c[F_TR(2)]));
-    if (!q.live) gk += fmaf(gYx, q.Yx, gYy * q.Yy);
-}
-
-// ---- Gauss-Newton mode ----------------------------------------------------------------------------
+// ---- Gauss-Newton mode, scalar formulation (used by the 8-column / affine variant) ---------------------
+// (the 6-column GN path and the gradient mode live in spb_gn_packed.cuh, written with packed FP32)
 // acc layout = upper triangle of the NPxNP pose block (row-major packed), g_p[NP], cost, wcost, nvalid
 // seg layout = B column [NP], D, g_d
 template <int NP, int NACC, int NSEG>
