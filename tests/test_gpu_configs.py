@@ -219,3 +219,46 @@ def test_depth_completion_against_reference_golden():
     avg, inv = render_segments_avg(kf, t("k"), t("visible"))
     assert np.array_equal(to_np(inv), z["invalid"])
     assert_close(to_np(avg), z["avg"], 1e-5, "average render vs reference")
+
+
+def test_edge_cases_empty_segment_many_segments_single_pixel():
+    """Edge cases the reference's dense formulation handles implicitly: a segment with an EMPTY mask, single-pixel
+    segments, and more segments than the kernel's shared-memory shift cache (N > 512 -> global fallback)."""
+    from oracle import ref_port as port
+    from super_primitive_b200 import dense_optim as do, synthetic as syn
+    from super_primitive_b200.depth_init import segment_based_depth_reinit
+    from super_primitive_b200.keyframe import KeyFrame
+    H, W, N = 48, 64, 600
+    g = torch.Generator().manual_seed(5)
+    masks = torch.zeros((N, H, W), dtype=torch.bool)
+    kp = torch.zeros((N, 2), dtype=torch.int64)
+    for b in range(N):
+        r, c = int(torch.randint(2, H - 2, (1,), generator=g)), int(torch.randint(2, W - 2, (1,), generator=g))
+        kp[b, 0], kp[b, 1] = r, c
+        if b % 7 == 0:
+            masks[b, r, c] = True                                  # single-pixel segment
+        elif b != 13:                                              # segment 13 stays EMPTY
+            masks[b, r - 1:r + 2, c - 2:c + 2] = True
+    x = (torch.arange(W, dtype=torch.float64) / W)[None, None, :].expand(N, H, W)
+    logd = ((0.1 * x) * masks).float()
+    src = KeyFrame(syn.sinus_image(H, W, noise=0.01, seed=1), syn.pinhole(H, W), logd, syn.normalise_rc(kp, (H, W)), masks)
+    trg = KeyFrame(syn.sinus_image(H, W, shift=(1.5, 0.5), noise=0.01, seed=2), syn.pinhole(H, W))
+    k0 = float(np.log(2.0)) + 0.05 * torch.randn(N, generator=g)
+    pose0 = syn.small_pose(0.02, 0.004, -0.003, 0.003, -0.002, 0.0015)
+    k, pose = _leaf(k0), _leaf(pose0)
+    ref = port.cost_single(src, trg, k, pose, CFG0)
+    ref['residual'].mean().backward()
+    kg, pg = _leaf(k0.cuda()), _leaf(pose0.cuda())
+    out = do.photomeric_cost(src.to("cuda"), trg.to("cuda"), kg, pg, CFG0)
+    out['residual'].mean().backward()
+    assert_close(to_np(out['residual']), to_np(ref['residual']), 2e-5, "residual")
+    assert_close(to_np(kg.grad), to_np(k.grad), 1e-3, "g_k")
+    assert float(kg.grad[13]) == 0.0 and float(k.grad[13]) == 0.0    # empty segment: no gradient
+    assert_close(to_np(pg.grad), to_np(pose.grad), 1e-3, "g_pose")
+    # re-initialisation with an empty segment: it is 'invisible' and takes the median of the visible ones
+    est = 1.5 + torch.rand((H, W), generator=g)
+    kk_ref, vis_ref = port.segment_median_reinit(est.clone(), src, 'median')
+    kk, vis = segment_based_depth_reinit(est.clone().cuda(), src.to("cuda"), 'median', return_info=True)
+    torch.set_grad_enabled(True)
+    assert np.array_equal(to_np(vis), to_np(vis_ref)) and not bool(vis[13])
+    assert_close(to_np(kk), to_np(kk_ref), 1e-5, "reinit with empty segment")
