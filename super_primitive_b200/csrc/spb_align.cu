@@ -361,9 +361,6 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
 #include "spb_gn_packed.cuh"
 #include "spb_lm.cuh"
 
-#ifndef SPB_BATCH2
-#define SPB_BATCH2 0
-#endif
 #ifndef SPB_UNROLL
 #define SPB_UNROLL 1                           // unroll factor of the per-lane point loop
 #endif
@@ -447,32 +444,6 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
         pseg.zero();
         // padding entries of a partial tile are zero words: uv bit 31 clear => invalid, no bounds test needed
         (void)cnt;
-#if SPB_BATCH2
-        // experiment: two points per lane in flight (both projections, then both gathers, then both updates)
-        SPB_PRAGMA_UNROLL(SPB_UNROLL)
-        for (int j = 0; j < SPB_PPT; j += 2) {
-            const int ia = j * 32 + lane, ib = ia + 32;
-            Proj qa, qb;
-            bool oka = project_point(c, s_uv[ia], s_f[SPB_TILE + ia], shift, Wl, qa);
-            bool okb = project_point(c, s_uv[ib], s_f[SPB_TILE + ib], shift, Wl, qb);
-            if constexpr (PACKED) { oka = oka && qa.live; okb = okb && qb.live; }
-            Taps4 ta, tb;
-            if (oka) load_taps(trg, Wl, qa.off, ta);
-            if (okb) load_taps(trg, Wl, qb.off, tb);
-            if (oka) {
-                const float i0 = s_f[2 * SPB_TILE + ia], i1 = s_f[3 * SPB_TILE + ia], i2 = s_f[4 * SPB_TILE + ia];
-                if constexpr (MODE == MODE_GRAD) point_grad_packed<AFF>(c, ta, qa, i0, i1, i2, gacc, seg[0]);
-                else if constexpr (PACKED) point_gn6_packed<AFF>(c, ta, qa, i0, i1, i2, irls_eps, pacc, pseg);
-                else point_gn<NP, NACC, NSEG>(c, ta, qa, i0, i1, i2, irls_eps, acc, seg);
-            }
-            if (okb) {
-                const float i0 = s_f[2 * SPB_TILE + ib], i1 = s_f[3 * SPB_TILE + ib], i2 = s_f[4 * SPB_TILE + ib];
-                if constexpr (MODE == MODE_GRAD) point_grad_packed<AFF>(c, tb, qb, i0, i1, i2, gacc, seg[0]);
-                else if constexpr (PACKED) point_gn6_packed<AFF>(c, tb, qb, i0, i1, i2, irls_eps, pacc, pseg);
-                else point_gn<NP, NACC, NSEG>(c, tb, qb, i0, i1, i2, irls_eps, acc, seg);
-            }
-        }
-#else
         SPB_PRAGMA_UNROLL(SPB_UNROLL)
         for (int j = 0; j < SPB_PPT; ++j) {
             const int i = j * 32 + lane;
@@ -491,7 +462,6 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
                     point_gn<NP, NACC, NSEG>(c, tp, q, i0, i1, i2, irls_eps, acc, seg);
             }
         }
-#endif
         if constexpr (PACKED) pseg.store(seg);
         tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
         __syncwarp();                                      // every lane is done with this slot
