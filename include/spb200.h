@@ -127,9 +127,12 @@ int spb_build_tile_pack(const SpbGeom* geom, const float* src_rgb, uint32_t* pac
  *   pairs      : HOST array of B pair descriptors (B <= 16), passed to the kernel by value
  *   work       : device workspace, spb_workspace_floats(geom, B, 0) floats
  *   out_pair   : [B][SPB_PAIR_NOUT]      out_gk : [B][n_seg] d cost_j / d k_b
+ *   out_pose   : NULL or [B][16]: d cost_j / d pose_j as a row-major 4x4 (bottom row zero)
+ *   out_flag   : NULL or [B]: 1.0 if the pair's outputs AND inputs (pose, k) are all finite, else 0.0 -- the
+ *                reference's five finiteness asserts per call folded into one device-side flag
  *   stats      : NULL or per-point outputs                                                      */
 int spb_cost_grad(const SpbGeom* geom, const SpbPair* pairs, int B, float* work, float* out_pair,
-                  float* out_gk, const SpbStats* stats, void* stream);
+                  float* out_gk, float* out_pose, float* out_flag, const SpbStats* stats, void* stream);
 
 /* Same for pre-lifted points (tracking): photomeric_cost_precomputed, core/dense_optim.py:365-403.
  * src_pts [P][3], src_px [3][P] planar, src_ok [P]; dims = geometry grid (H,W) used for

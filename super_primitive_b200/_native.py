@@ -56,7 +56,7 @@ _PROTOS = {
     "spb_pack_rgba": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
     "spb_sample_source": (_i, [C.POINTER(SpbGeom), _vp, _i, _i, _vp, _vp]),
     "spb_build_tile_pack": (_i, [C.POINTER(SpbGeom), _vp, _vp, _vp]),
-    "spb_cost_grad": (_i, [C.POINTER(SpbGeom), C.POINTER(SpbPair), _i, _vp, _vp, _vp,
+    "spb_cost_grad": (_i, [C.POINTER(SpbGeom), C.POINTER(SpbPair), _i, _vp, _vp, _vp, _vp, _vp,
                            C.POINTER(SpbStats), _vp]),
     "spb_cost_grad_points": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SpbPair), _vp, _vp, _vp]),
     "spb_workspace_floats": (_i64, [C.POINTER(SpbGeom), _i, _i]),

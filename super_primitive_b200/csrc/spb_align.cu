@@ -20,6 +20,10 @@
 
 enum { MODE_GRAD = 0, MODE_GN = 1 };
 
+struct PairPack {        // up to 16 pair descriptors passed by value (Python per-call path)
+    SpbPair p[16];
+};
+
 template <int NACC>
 __device__ __forceinline__ void block_reduce_store(float (&acc)[NACC], float* s_red, float* dst) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -474,9 +478,6 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     block_reduce_store<NACC>(acc, s_red, part_pair + (size_t)blockIdx.x * NACC);
 }
 
-struct PairPack {
-    SpbPair p[16];
-};
 
 // occupancy target: 3 CTAs/SM (<= 80 registers) for the gradient kernel, 2 for the GN kernel whose
 // 38 accumulators do not fit 80 registers without spilling
@@ -545,27 +546,41 @@ __device__ __forceinline__ float grad_col_scale(int idx, const float* K, bool sc
     return col == 0 ? 1.0f / K[0] : (col == 1 ? 1.0f / K[4] : 1.0f);
 }
 
-__global__ void k_finalize_grad(const __grid_constant__ SpbGeom g, int ctas, int scale_cols,
-                                const float* __restrict__ work, float* __restrict__ out_pair,
-                                float* __restrict__ out_gk) {
+__global__ void k_finalize_grad(const __grid_constant__ SpbGeom g, const __grid_constant__ PairPack pack, int ctas,
+                                int scale_cols, const float* __restrict__ work, float* __restrict__ out_pair,
+                                float* __restrict__ out_gk, float* __restrict__ out_pose, float* __restrict__ out_flag) {
     const int pair = blockIdx.x;
     const size_t stride = (size_t)ctas * SPB_PAIR_NOUT + (size_t)g.n_tiles;
     const float* pp = work + pair * stride;
     const float* ps = pp + (size_t)ctas * SPB_PAIR_NOUT;
     const float norm = 1.0f / (3.0f * (float)g.n_pts);
+    __shared__ float s_v[SPB_PAIR_NOUT];
+    bool finite = true;
     if (threadIdx.x < SPB_PAIR_NOUT) {
         float v = 0.f;
         for (int cta = 0; cta < ctas; ++cta) v += pp[(size_t)cta * SPB_PAIR_NOUT + threadIdx.x];
         v *= grad_col_scale(threadIdx.x, g.K, scale_cols != 0);
-        out_pair[pair * SPB_PAIR_NOUT + threadIdx.x] = (threadIdx.x == 15) ? v : v * norm;
+        v = (threadIdx.x == 15) ? v : v * norm;
+        out_pair[pair * SPB_PAIR_NOUT + threadIdx.x] = v;
+        s_v[threadIdx.x] = v;
+        finite = isfinite(v) && isfinite(pack.p[pair].pose[threadIdx.x]);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int b = warp; b < g.n_seg; b += nwarps) {
         float v = 0.f;
         const int t1 = g.seg_tile[b + 1];
         for (int t = g.seg_tile[b] + lane; t < t1; t += 32) v += ps[t];
-        v = warp_sum(v);
-        if (lane == 0) out_gk[(size_t)pair * g.n_seg + b] = v * norm;
+        v = warp_sum(v) * norm;
+        if (lane == 0) out_gk[(size_t)pair * g.n_seg + b] = v;
+        finite = finite && isfinite(v) && isfinite(pack.p[pair].k[b]);
+    }
+    // the reference's finiteness asserts (core/dense_optim.py:44,78,311,321,340-343), folded into one flag per pair
+    const int all_ok = __syncthreads_and(finite ? 1 : 0);
+    if (out_flag && threadIdx.x == 0) out_flag[pair] = all_ok ? 1.0f : 0.0f;
+    // d cost / d pose as the 4x4 the autograd boundary hands back (bottom row zero)
+    if (out_pose && threadIdx.x < 16) {
+        const int r = threadIdx.x >> 2, cc = threadIdx.x & 3;
+        out_pose[pair * 16 + threadIdx.x] = (r == 3) ? 0.f : (cc == 3 ? s_v[1 + r] : s_v[4 + 3 * r + cc]);
     }
 }
 
@@ -759,7 +774,7 @@ extern "C" int64_t spb_workspace_floats(const SpbGeom* geom, int B, int gn) {
 extern "C" int64_t spb_workspace_floats_points(int P) { return (int64_t)ctas_for_points(P) * SPB_PAIR_NOUT; }
 
 extern "C" int spb_cost_grad(const SpbGeom* geom, const SpbPair* pairs, int B, float* work, float* out_pair,
-                             float* out_gk, const SpbStats* stats, void* stream) {
+                             float* out_gk, float* out_pose, float* out_flag, const SpbStats* stats, void* stream) {
     if (!geom || !pairs || B < 1 || !work || !out_pair || !out_gk) return SPB_EINVAL;
     if (B > 16) return SPB_ELIMIT;
     if (geom->n_pts <= 0 || geom->n_tiles <= 0) return SPB_EINVAL;
@@ -789,7 +804,7 @@ extern "C" int spb_cost_grad(const SpbGeom* geom, const SpbPair* pairs, int B, f
         }
     }
     SPB_CHECK_LAUNCH();
-    k_finalize_grad<<<B, 256, 0, st>>>(*geom, ctas, stats ? 0 : 1, work, out_pair, out_gk);
+    k_finalize_grad<<<B, 256, 0, st>>>(*geom, pack, ctas, stats ? 0 : 1, work, out_pair, out_gk, out_pose, out_flag);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

@@ -110,6 +110,7 @@ class CompactGeometry:
                              P, P_pad, N, T, H, W)
         self.cref = C.byref(self.c)
         self._levels = OrderedDict()     # source-sample caches per (image identity)
+        self._work = {}
 
     # ---- helpers -------------------------------------------------------------------------------
     def pad_index(self):
@@ -151,6 +152,15 @@ class CompactGeometry:
 
     def source_samples(self, image):
         return self.level_buffers(image)[0]
+
+    def workspace(self, n_pairs):
+        """Partial-sum scratch of the fused kernel for ``n_pairs`` pairs over this geometry (stream-ordered reuse)."""
+        ws = self._work.get(n_pairs)
+        if ws is None:
+            ws = torch.empty(nat.lib().spb_workspace_floats(self.cref, n_pairs, 0), dtype=torch.float32,
+                             device=self.uv.device)
+            self._work[n_pairs] = ws
+        return ws
 
     def bytes(self):
         return self.P_pad * 8 + self.n_tiles * 16 + self.N * 8

@@ -47,7 +47,7 @@ def test_argument_validation_without_gpu():
     lib = _native.lib()
     assert lib.spb_compact_count(None, 1, 4, 4, None, None) == -1
     assert lib.spb_pack_rgba(None, 0, 1, 4, 4, None, None) == -1
-    assert lib.spb_cost_grad(None, None, 1, None, None, None, None, None) == -1
+    assert lib.spb_cost_grad(None, None, 1, None, None, None, None, None, None, None) == -1
     assert lib.spb_gn_accumulate(None, None, None, 1, 1, 1e-3, 0, None, 0, None, None, None, None, None) == -1
     assert lib.spb_segment_reinit(None, None, 1, None, None, None, None, None) == -1
 
