@@ -79,10 +79,8 @@ typedef struct SpbStats {
     float*   trg_px;           /* [B][3][n]  after affine compensation                                */
     float*   residual_raw;     /* [B][3][n]                                                           */
     uint8_t* trg_ok;           /* [B][n]                                                              */
-    uint8_t* src_ok;           /* [n]                                                                 */
     int64_t* full_mask;        /* [B][n]                                                              */
-    int64_t* seg_ids;          /* [n]                                                                 */
-} SpbStats;
+} SpbStats;                    /* (source validity and segment ids come from spb_lift_points)          */
 
 /* ============================ geometry build (once per keyframe) ============================== */
 
@@ -101,9 +99,8 @@ int spb_compact_scan(const int32_t* row_cnt, int N, int H, int32_t* row_off, int
  * source-validity bit (core/dense_optim.py:128-130,146 applied to the point's own pixel).
  * logd_seg_stride = H*W for per-segment log-depth, 0 for a shared (H,W) map. */
 int spb_compact_fill(const uint8_t* masks, const float* logd, int64_t logd_seg_stride,
-                     const float* keypoints, const float* K, int N, int H, int W,
-                     const int32_t* row_off, const int32_t* seg_ptr_pad, uint32_t* uv, float* L,
-                     float* seg_lkp, int32_t* kp_rc, void* stream);
+                     const float* keypoints, int N, int H, int W, const int32_t* row_off, uint32_t* uv,
+                     float* L, float* seg_lkp, int32_t* kp_rc, void* stream);
 
 /* planar (3,Hl,Wl) -> RGBA-interleaved [Hl][Wl][4]; n_img images, src stride in floats. */
 int spb_pack_rgba(const float* planar, int64_t img_stride, int n_img, int Hl, int Wl, float* rgba,

@@ -44,15 +44,14 @@ class SpbPair(C.Structure):
 
 class SpbStats(C.Structure):
     _fields_ = [("src_pts", C.c_void_p), ("moved_pts", C.c_void_p), ("trg_px", C.c_void_p),
-                ("residual_raw", C.c_void_p), ("trg_ok", C.c_void_p), ("src_ok", C.c_void_p),
-                ("full_mask", C.c_void_p), ("seg_ids", C.c_void_p)]
+                ("residual_raw", C.c_void_p), ("trg_ok", C.c_void_p), ("full_mask", C.c_void_p)]
 
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _PROTOS = {
     "spb_compact_count": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "spb_compact_scan": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "spb_compact_fill": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spb_compact_fill": (_i, [_vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spb_pack_rgba": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
     "spb_sample_source": (_i, [C.POINTER(SpbGeom), _vp, _i, _i, _vp, _vp]),
     "spb_build_tile_pack": (_i, [C.POINTER(SpbGeom), _vp, _vp, _vp]),

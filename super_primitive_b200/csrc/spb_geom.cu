@@ -60,8 +60,8 @@ __global__ void k_row_scan(const int32_t* __restrict__ row_cnt, int N, int H, in
 
 // pass 3: ordered scatter, one warp per (segment,row)
 __global__ void k_row_fill(const uint8_t* __restrict__ masks, const float* __restrict__ logd, int64_t seg_stride,
-                           const float* __restrict__ K, int N, int H, int W, const int32_t* __restrict__ row_off,
-                           uint32_t* __restrict__ uv, float* __restrict__ L) {
+                           int N, int H, int W, const int32_t* __restrict__ row_off, uint32_t* __restrict__ uv,
+                           float* __restrict__ L) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= N * H) return;
@@ -126,15 +126,12 @@ extern "C" int spb_compact_scan(const int32_t* row_cnt, int N, int H, int32_t* r
 }
 
 extern "C" int spb_compact_fill(const uint8_t* masks, const float* logd, int64_t logd_seg_stride,
-                                const float* keypoints, const float* K, int N, int H, int W, const int32_t* row_off,
-                                const int32_t* seg_ptr_pad, uint32_t* uv, float* L, float* seg_lkp, int32_t* kp_rc,
-                                void* stream) {
+                                const float* keypoints, int N, int H, int W, const int32_t* row_off, uint32_t* uv,
+                                float* L, float* seg_lkp, int32_t* kp_rc, void* stream) {
     if (!masks || !logd || !keypoints || !row_off || !uv || !L || !seg_lkp || !kp_rc) return SPB_EINVAL;
-    (void)seg_ptr_pad;
-    (void)K;
     const int rows = N * H;
     cudaStream_t st = (cudaStream_t)stream;
-    k_row_fill<<<(rows + 7) / 8, 256, 0, st>>>(masks, logd, logd_seg_stride, K, N, H, W, row_off, uv, L);
+    k_row_fill<<<(rows + 7) / 8, 256, 0, st>>>(masks, logd, logd_seg_stride, N, H, W, row_off, uv, L);
     SPB_CHECK_LAUNCH();
     k_keypoints<<<(N + 127) / 128, 128, 0, st>>>(keypoints, logd, logd_seg_stride, N, H, W, seg_lkp, kp_rc);
     SPB_CHECK_LAUNCH();

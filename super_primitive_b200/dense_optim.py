@@ -218,7 +218,7 @@ def _point_stats(geom, src_image, level, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_
     def make(done, nb):
         n = P
         return nat.SpbStats(src_pts.data_ptr(), moved[done:].data_ptr(), trg_px[done:].data_ptr(),
-                            raw[done:].data_ptr(), trg_ok[done:].data_ptr(), None, full[done:].data_ptr(), None)
+                            raw[done:].data_ptr(), trg_ok[done:].data_ptr(), full[done:].data_ptr())
 
     _launch_pairs(geom, level, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau, stats=make)
     idx = geom.pad_index()

@@ -82,9 +82,8 @@ class CompactGeometry:
         self.seg_lkp = torch.empty(N, dtype=torch.float32, device=dev)
         self.kp_rc = torch.empty((N, 2), **i32)
         nat.check(lib.spb_compact_fill(m8.data_ptr(), logd_c.data_ptr(), H * W if per_seg else 0, kps.data_ptr(),
-                                       self.K.data_ptr(), N, H, W, row_off.data_ptr(), seg_ptr_pad.data_ptr(),
-                                       self.uv.data_ptr(), self.logd.data_ptr(), self.seg_lkp.data_ptr(),
-                                       self.kp_rc.data_ptr(), st), "spb_compact_fill")
+                                       N, H, W, row_off.data_ptr(), self.uv.data_ptr(), self.logd.data_ptr(),
+                                       self.seg_lkp.data_ptr(), self.kp_rc.data_ptr(), st), "spb_compact_fill")
         # tile table (host, once): tiles never straddle segments
         cnt = sp[1:] - sp[:-1]
         ntile = (cnt + nat.TILE - 1) // nat.TILE

@@ -38,7 +38,7 @@ def test_struct_layouts_match_header_sizes():
     from super_primitive_b200 import _native
     assert ctypes.sizeof(_native.SpbGeom) == 6 * 8 + 6 * 4
     assert ctypes.sizeof(_native.SpbPair) == 8 * 8 + 4 * 4
-    assert ctypes.sizeof(_native.SpbStats) == 8 * 8
+    assert ctypes.sizeof(_native.SpbStats) == 6 * 8
 
 
 def test_argument_validation_without_gpu():
