@@ -175,9 +175,19 @@ __device__ __forceinline__ void point_grad_packed(const float* __restrict__ c, c
     for (int ch = 0; ch < 3; ++ch) {
         const float r = AFF ? (Is[ch] - fmaf(c[F_EA], I[ch], c[F_BB])) : (Is[ch] - I[ch]);
         cost += fabsf(r);
-        const float s = (r > 0.f) ? 1.0f : ((r < 0.f) ? -1.0f : 0.0f);
-        gxy = fma2(s, d[ch], gxy);
-        if (AFF) { ga = fmaf(s, I[ch], ga); gb += s; }
+        if constexpr (AFF) {
+            const float s = (r > 0.f) ? 1.0f : ((r < 0.f) ? -1.0f : 0.0f);
+            gxy = fma2(s, d[ch], gxy);
+            ga = fmaf(s, I[ch], ga);
+            gb += s;
+        } else {
+            // sign(r) * (dIx, dIy): XOR r's sign bit into the slope pair (one LOP3 each); sign(0) = 0 contributes
+            // nothing, exactly like torch.sign in the reference's backward
+            const uint32_t sb = __float_as_uint(r) & 0x80000000u;
+            const float2 sd = make_float2(__uint_as_float(__float_as_uint(d[ch].x) ^ sb),
+                                          __uint_as_float(__float_as_uint(d[ch].y) ^ sb));
+            if (r != 0.f) gxy = __fadd2_rn(gxy, sd);
+        }
     }
     // d cost / d (x_, y_) = (cu gx, cv gy);  gY = rho (gx_, gy_, -(gx_ x_ + gy_ y_))
     const float2 gb2 = __fmul2_rn(gxy, *reinterpret_cast<const float2*>(c + F_CU));

@@ -169,3 +169,37 @@ def two_frame_problem(H, W, N, kind="strips", seed=0, noise=0.0, shift=(2.0, 1.0
     # and float32 rounding (in the reference too) decides which side is taken
     pose0 = small_pose(0.02, 0.004, -0.003, 0.003, -0.002, 0.0015)
     return src, trg, k0, pose0
+
+
+def planar_scene_pair(H, W, N, pose_true, z0=2.0, kind="strips", seed=0):
+    """A geometrically CONSISTENT two-frame problem: a fronto-parallel textured plane at depth ``z0`` in the source
+    frame, rendered exactly (analytic texture, ray/plane intersection) into the source view and into the view
+    ``pose_true`` (source -> target).  Aligning the two must recover ``pose_true`` (up to the joint scale of
+    translation and depth).  Returns (src keyframe, target frame, true log-depth seeds)."""
+    K = pinhole(H, W, torch.float64)
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+
+    def tex(X, Y):
+        chans = []
+        for c in range(3):
+            ph = 2 * math.pi * c / 3.0
+            chans.append(0.5 + 0.3 * torch.sin(2 * math.pi * (1.5 * X + 1.0 * Y) + ph)
+                         + 0.15 * torch.sin(2 * math.pi * (-0.9 * X + 2.3 * Y) + 1.7 * ph))
+        return torch.stack(chans, 0)
+
+    v, u = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
+    src_img = tex((u - cx) * z0 / fx, (v - cy) * z0 / fy)
+    T = pose_true.to(torch.float64)
+    R, t = T[:3, :3], T[:3, 3]
+    d = torch.stack([(u - cx) / fx, (v - cy) / fy, torch.ones_like(u)], -1)          # target-frame rays
+    Rt_d = d @ R                                                                       # (R^T d) per pixel
+    Rt_t = R.T @ t
+    lam = (z0 + Rt_t[2]) / Rt_d[..., 2]
+    Ps = lam[..., None] * Rt_d - Rt_t                                                  # R^T (lam d - t)
+    trg_img = tex(Ps[..., 0], Ps[..., 1])
+    masks, kp = segment_masks(H, W, N, kind, seed)
+    logd = torch.zeros((N, H, W), dtype=torch.float32)                                 # plane: constant depth
+    src = KeyFrame(src_img.float(), K.float(), logd, normalise_rc(kp, (H, W)), masks)
+    trg = KeyFrame(trg_img.float(), K.float())
+    k_true = torch.full((N,), math.log(z0), dtype=torch.float32)
+    return src, trg, k_true
