@@ -29,7 +29,10 @@ extern "C" {
 #define SPB_EINVAL (-1)
 #define SPB_ELIMIT (-2)
 
-#define SPB_TILE 128          /* points per warp-tile (one segment per tile)            */
+#ifndef SPB_TILE
+#define SPB_TILE 128          /* points per warp-tile (one segment per tile); compile-time tunable, a multiple of 32;
+                                 the host reads the built value through spb_tile_points()                  */
+#endif
 #define SPB_PACK_WORDS (4 + 5 * SPB_TILE)   /* words per tile block: {seg,cnt,ustart,0} + 5 arrays */
 #define SPB_PAD 4             /* every segment's point range is padded to this multiple  */
 #define SPB_PAIR_NOUT 16      /* floats per pair, gradient mode (layout below)           */
@@ -236,6 +239,9 @@ int spb_lift_points(const SpbGeom* geom, const float* k, float* src_pts, int64_t
  * est_depth [H][W]; seg_val [N] scratch; visible [N] out; out_k [N] out; n_visible [1] out (may be NULL). */
 int spb_segment_reinit(const SpbGeom* geom, const float* est_depth, int mode, float* seg_val,
                        uint8_t* visible, float* out_k, int32_t* n_visible, void* stream);
+
+/* points per tile the library was built with (SPB_TILE): the host sizes tile tables and level buffers with it */
+int spb_tile_points(void);
 
 /* version / build info */
 int spb_version(void);

@@ -75,6 +75,7 @@ _PROTOS = {
     "spb_pyr_down": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "spb_lift_points": (_i, [C.POINTER(SpbGeom), _vp, _vp, _vp, _vp, _vp]),
     "spb_segment_reinit": (_i, [C.POINTER(SpbGeom), _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "spb_tile_points": (_i, []),
     "spb_version": (_i, []),
 }
 
@@ -102,6 +103,9 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        global TILE, PACK_WORDS
+        TILE = int(handle.spb_tile_points())      # the tile size is a build-time constant of the library
+        PACK_WORDS = 4 + 5 * TILE
     return _lib
 
 

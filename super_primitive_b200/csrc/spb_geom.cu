@@ -541,4 +541,6 @@ extern "C" int spb_depth_splat_points(const float* pts, int P, const float* K, i
     return SPB_OK;
 }
 
-extern "C" int spb_version(void) { return 101; }
+extern "C" int spb_tile_points(void) { return SPB_TILE; }
+
+extern "C" int spb_version(void) { return 102; }
