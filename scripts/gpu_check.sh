@@ -19,7 +19,7 @@ if [ "$3" != "" ]; then
   done
 fi
 if [ "$2" != "noprof" ]; then
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_align|k_finalize|k_lm" -c 40 --csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_align|finalize|k_lm" -c 40 --csv \
     --log-file $OUT/launches_$TAG.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_list_$TAG.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_align_global -s 3 -c 1 -f -o $OUT/prof_gn_$TAG \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_gn_$TAG.log 2>&1

@@ -375,6 +375,15 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
 // Hot-path body: per-warp bulk-async pipelines (see spb_fast.cuh).  grid = (ctas_per_pair, pairs)
 //   part_pair : [cta][NACC]      part_seg : [tile][NSEG]
 // ------------------------------------------------------------------------------------------------
+#ifndef SPB_TRG_PREFETCH
+#define SPB_TRG_PREFETCH 0                      // 1: per-line L2 prefetch of the target image, 2: bulk (TMA) prefetch
+#endif
+#ifndef SPB_CTA_CONTIG
+#define SPB_CTA_CONTIG 0                        // 1: contiguous tile run per CTA instead of CTA-strided tiles
+#endif
+#ifndef SPB_PACK_EVICT
+#define SPB_PACK_EVICT 0                        // 1: evict-first L2 hint on the tile-stream copies
+#endif
 template <int MODE, int NP, bool AFF>
 __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair& pr, float irls_eps,
                                                 float* __restrict__ part_pair, float* __restrict__ part_seg) {
@@ -399,21 +408,54 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     __syncthreads();
     const float* c = s_ctx;
 
+#if SPB_CTA_CONTIG
+    // every CTA owns one contiguous run of tiles, its warps march through it side by side
+    const int per = ((g.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x + SPB_WARPS - 1) / SPB_WARPS * SPB_WARPS;
+    const int WS = SPB_WARPS;
+    const int t_first = blockIdx.x * per + warp;
+    const int t_end = min(g.n_tiles, (int)(blockIdx.x + 1) * per);
+#else
     const int WS = gridDim.x * SPB_WARPS;                  // tile stride of this warp
     const int t_first = blockIdx.x * SPB_WARPS + warp;
+    const int t_end = g.n_tiles;
+#endif
     const uint32_t* pack = pr.tile_pack;
 
     // producer (lane 0): ONE bulk copy brings the whole tile block (header + uv + logd + r + g + b)
+#if SPB_PACK_EVICT
+    const uint64_t pol = l2_policy_evict_first();
+#endif
     auto issue = [&](int t, int slot) {
         const uint32_t bar = smem_u32(bars + slot);
         mbar_expect_tx(bar, SPB_PACK_WORDS * 4u);
+#if SPB_PACK_EVICT
+        bulk_g2s_hint(smem_u32(ring + slot * SPB_SLOT_WORDS), pack + (size_t)t * SPB_PACK_WORDS, SPB_PACK_WORDS * 4u, bar,
+                      pol);
+#else
         bulk_g2s(smem_u32(ring + slot * SPB_SLOT_WORDS), pack + (size_t)t * SPB_PACK_WORDS, SPB_PACK_WORDS * 4u, bar);
+#endif
     };
+#if SPB_TRG_PREFETCH == 1
+    {   // pull the pair's target image towards L2 while the first tiles are in flight: the gathers of the
+        // tile loop then pay L2 latency instead of DRAM latency (the CTAs of a pair share the work)
+        const char* tb = reinterpret_cast<const char*>(pr.trg_rgba);
+        const int nlines = (pr.Hl * pr.Wl * 16 + 127) >> 7;
+        for (int l = blockIdx.x * SPB_THREADS + threadIdx.x; l < nlines; l += gridDim.x * SPB_THREADS)
+            prefetch_l2_line(tb + ((size_t)l << 7));
+    }
+#elif SPB_TRG_PREFETCH == 2
+    if (lane == 0) {
+        const char* tb = reinterpret_cast<const char*>(pr.trg_rgba);
+        const int nchunks = (pr.Hl * pr.Wl * 16) >> 12;          // 4 KB chunks (tail left to demand loads)
+        for (int l = blockIdx.x * SPB_WARPS + warp; l < nchunks; l += gridDim.x * SPB_WARPS)
+            prefetch_l2_bulk(tb + ((size_t)l << 12), 4096u);
+    }
+#endif
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < SPB_WSTAGES - 1; ++s) {
             const int t = t_first + s * WS;
-            if (t < g.n_tiles) issue(t, s);
+            if (t < t_end) issue(t, s);
         }
     }
 
@@ -430,10 +472,10 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
 
     int slot = 0, fill = SPB_WSTAGES - 1;                  // slot consumed now / slot refilled now
     uint32_t phase = 0;
-    for (int t = t_first; t < g.n_tiles; t += WS) {
+    for (int t = t_first; t < t_end; t += WS) {
         if (lane == 0) {
             const int tn = t + (SPB_WSTAGES - 1) * WS;
-            if (tn < g.n_tiles) issue(tn, fill);
+            if (tn < t_end) issue(tn, fill);
         }
         mbar_wait(smem_u32(bars + slot), phase);
         const uint32_t* sl = ring + slot * SPB_SLOT_WORDS;
@@ -535,6 +577,51 @@ k_align_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pa
     align_body_warp<MODE, NP, AFF>(s_g, s_pr, irls_eps, base, base + (size_t)gridDim.x * NACC);
 }
 
+// Fixed-order sum of the per-tile partials of TWO segments at once (tiles [ta0,ta1) and [tb0,tb1), NSEG floats per
+// tile, contiguous).  Lanes walk the contiguous float range coalesced: lane l < G*NSEG always meets value l % NSEG
+// (G = 32 / NSEG tiles per round), so one register per segment accumulates; the G lanes holding the same value
+// are then combined in fixed order.  Result valid in lanes < NSEG.  Two segments interleaved = two independent
+// load streams in flight per warp (the finalize kernels are latency-bound: one CTA per problem).
+template <int NSEG>
+__device__ __forceinline__ void seg_sum2(const float* ps, int ta0, int ta1, int tb0, int tb1, int lane, float& ra,
+                                         float& rb) {
+    constexpr int G = 32 / NSEG, STRIDE = G * NSEG;
+    constexpr int U = 16;                       // loads in flight per lane and segment (the kernel is latency-bound)
+    float va = 0.f, vb = 0.f;
+    if (lane < STRIDE) {
+        const float* pa = ps + (size_t)ta0 * NSEG + lane;
+        const float* pb = ps + (size_t)tb0 * NSEG + lane;
+        const int na = (ta1 - ta0) * NSEG - lane, nb = (tb1 - tb0) * NSEG - lane;   // elements left for this lane
+        const int nmax = max(na, nb);
+        for (int e0 = 0; e0 < nmax; e0 += U * STRIDE) {
+            float ba[U], bb[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * STRIDE;
+                ba[u] = (e < na) ? pa[e] : 0.f;
+                bb[u] = (e < nb) ? pb[e] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                va += ba[u];
+                vb += bb[u];
+            }
+        }
+    }
+    if constexpr (NSEG == 1) {
+        ra = warp_sum(va);
+        rb = warp_sum(vb);
+    } else {
+        ra = va;
+        rb = vb;
+#pragma unroll
+        for (int gi = 1; gi < G; ++gi) {
+            ra += __shfl_sync(0xffffffffu, va, (lane + gi * NSEG) & 31);
+            rb += __shfl_sync(0xffffffffu, vb, (lane + gi * NSEG) & 31);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // finalize: fixed-order reduction of the partials
 // ------------------------------------------------------------------------------------------------
@@ -566,13 +653,20 @@ __global__ void k_finalize_grad(const __grid_constant__ SpbGeom g, const __grid_
         finite = isfinite(v) && isfinite(pack.p[pair].pose[threadIdx.x]);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int b = warp; b < g.n_seg; b += nwarps) {
-        float v = 0.f;
-        const int t1 = g.seg_tile[b + 1];
-        for (int t = g.seg_tile[b] + lane; t < t1; t += 32) v += ps[t];
-        v = warp_sum(v) * norm;
-        if (lane == 0) out_gk[(size_t)pair * g.n_seg + b] = v;
+    for (int b = warp; b < g.n_seg; b += 2 * nwarps) {
+        const int b2 = b + nwarps;
+        const bool two = b2 < g.n_seg;
+        float v, v2;
+        seg_sum2<1>(ps, g.seg_tile[b], g.seg_tile[b + 1], two ? g.seg_tile[b2] : 0, two ? g.seg_tile[b2 + 1] : 0, lane,
+                    v, v2);
+        v *= norm;
+        v2 *= norm;
+        if (lane == 0) {
+            out_gk[(size_t)pair * g.n_seg + b] = v;
+            if (two) out_gk[(size_t)pair * g.n_seg + b2] = v2;
+        }
         finite = finite && isfinite(v) && isfinite(pack.p[pair].k[b]);
+        if (two) finite = finite && isfinite(v2) && isfinite(pack.p[pair].k[b2]);
     }
     // the reference's finiteness asserts (core/dense_optim.py:44,78,311,321,340-343), folded into one flag per pair
     const int all_ok = __syncthreads_and(finite ? 1 : 0);
@@ -637,27 +731,21 @@ __device__ __forceinline__ void finalize_gn_body(const SpbGeom* __restrict__ geo
     if (NP == 8 && threadIdx.x == SPB_GN_PAIR_NOUT - 1) op[threadIdx.x] = 0.f;
     const int so = seg_off[pair];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int b = warp; b < g.n_seg; b += nwarps) {          // one warp per segment, lanes stride its tiles
-        float v[NSEG];
-#pragma unroll
-        for (int i = 0; i < NSEG; ++i) v[i] = 0.f;
-        const int t1 = g.seg_tile[b + 1];
-        for (int t = g.seg_tile[b] + lane; t < t1; t += 32) {
-#pragma unroll
-            for (int i = 0; i < NSEG; ++i) v[i] += ps[(size_t)t * NSEG + i];
-        }
-#pragma unroll
-        for (int i = 0; i < NSEG; ++i) v[i] = warp_sum(v[i]);
-        if (lane == 0) {
-            float* os = out_seg + (size_t)(so + b) * SPB_GN_SEG_NOUT;
-            if (NP == 8) {
-#pragma unroll
-                for (int i = 0; i < 10; ++i) os[i] = v[i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) os[i] = v[i];
-                os[6] = 0.f; os[7] = 0.f; os[8] = v[6]; os[9] = v[7];
-            }
+    // two segments per warp per round; lane i < NSEG ends up with value i of the segment (seg_sum2)
+    for (int b = warp; b < g.n_seg; b += 2 * nwarps) {
+        const int b2 = b + nwarps;
+        const bool two = b2 < g.n_seg;
+        float v, v2;
+        seg_sum2<NSEG>(ps, g.seg_tile[b], g.seg_tile[b + 1], two ? g.seg_tile[b2] : 0, two ? g.seg_tile[b2 + 1] : 0,
+                       lane, v, v2);
+        // fixed 10-float record: B[0..7], D, g_d (the 6-column accumulation leaves B[6], B[7] zero)
+        const int slot = (NP == 8) ? lane : (lane < 6 ? lane : lane + 2);
+        if (lane < NSEG) {
+            out_seg[(size_t)(so + b) * SPB_GN_SEG_NOUT + slot] = v;
+            if (two) out_seg[(size_t)(so + b2) * SPB_GN_SEG_NOUT + slot] = v2;
+        } else if (NP == 6 && lane < 10) {                   // lanes 8, 9 -> slots 6, 7
+            out_seg[(size_t)(so + b) * SPB_GN_SEG_NOUT + lane - 2] = 0.f;
+            if (two) out_seg[(size_t)(so + b2) * SPB_GN_SEG_NOUT + lane - 2] = 0.f;
         }
     }
 }
@@ -670,8 +758,11 @@ __global__ void k_finalize_gn(const SpbGeom* __restrict__ geoms, const SpbPair* 
 }
 
 // finalize + damped solve + retraction in ONE launch (one CTA per problem): the second kernel of a GN iteration
+#ifndef SPB_FIN_THREADS
+#define SPB_FIN_THREADS 512
+#endif
 template <int NP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SPB_FIN_THREADS)
 k_gn_finalize_solve(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
                     const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_cnt, int ctas,
                     const float* __restrict__ work, int64_t work_stride, float* gn_pair, float* gn_seg,
@@ -892,11 +983,11 @@ extern "C" int spb_gn_iterate(const SpbGeom* geoms, const SpbPair* pairs, const 
     if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
     const int opt_aff = with_affine == 1 ? 1 : 0;
     if (with_affine == 1)
-        k_gn_finalize_solve<8><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, seg_cnt, ctas, work, work_stride, gn_pair,
+        k_gn_finalize_solve<8><<<n_pairs, SPB_FIN_THREADS, 0, st>>>(geoms, pairs, seg_off, seg_cnt, ctas, work, work_stride, gn_pair,
                                                         gn_seg, opt_aff, poses, k, aff_trg, lm_state, saved_pair,
                                                         saved_seg);
     else
-        k_gn_finalize_solve<6><<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, seg_cnt, ctas, work, work_stride, gn_pair,
+        k_gn_finalize_solve<6><<<n_pairs, SPB_FIN_THREADS, 0, st>>>(geoms, pairs, seg_off, seg_cnt, ctas, work, work_stride, gn_pair,
                                                         gn_seg, opt_aff, poses, k, aff_trg, lm_state, saved_pair,
                                                         saved_seg);
     SPB_CHECK_LAUNCH();
@@ -920,12 +1011,16 @@ __global__ void k_finalize_grad_global(const SpbGeom* __restrict__ geoms, const 
     }
     const int so = seg_off[pair];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int b = warp; b < g.n_seg; b += nwarps) {
-        float v = 0.f;
-        const int t1 = g.seg_tile[b + 1];
-        for (int t = g.seg_tile[b] + lane; t < t1; t += 32) v += ps[t];
-        v = warp_sum(v);
-        if (lane == 0) out_gk[so + b] = v * norm;
+    for (int b = warp; b < g.n_seg; b += 2 * nwarps) {
+        const int b2 = b + nwarps;
+        const bool two = b2 < g.n_seg;
+        float v, v2;
+        seg_sum2<1>(ps, g.seg_tile[b], g.seg_tile[b + 1], two ? g.seg_tile[b2] : 0, two ? g.seg_tile[b2 + 1] : 0, lane,
+                    v, v2);
+        if (lane == 0) {
+            out_gk[so + b] = v * norm;
+            if (two) out_gk[so + b2] = v2 * norm;
+        }
     }
 }
 

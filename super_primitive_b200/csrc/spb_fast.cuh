@@ -53,6 +53,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// same copy with an L2 eviction-priority hint (the tile stream is read exactly once per launch)
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                              uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void prefetch_l2_line(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
@@ -146,12 +165,24 @@ __device__ __forceinline__ bool project_point(const float* __restrict__ c, uint3
 }
 
 // the four RGBA taps of one point; issued early (software pipelining), consumed by point_grad / point_gn
+#ifndef SPB_TAP_L2_256
+#define SPB_TAP_L2_256 1                        // 1: gathers ask L2 to fill 256-byte granules on a miss
+#endif
+__device__ __forceinline__ float4 ldg_l2_256(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 struct Taps4 {
     float4 nw, ne, sw, se;
 };
 __device__ __forceinline__ void load_taps(const float4* __restrict__ trg, int Wl, int off, Taps4& t) {
     const float4* p0 = trg + off;
+#if SPB_TAP_L2_256
+    t.nw = ldg_l2_256(p0); t.ne = ldg_l2_256(p0 + 1); t.sw = ldg_l2_256(p0 + Wl); t.se = ldg_l2_256(p0 + Wl + 1);
+#else
     t.nw = __ldg(p0); t.ne = __ldg(p0 + 1); t.sw = __ldg(p0 + Wl); t.se = __ldg(p0 + Wl + 1);
+#endif
 }
 
 // ---- Gauss-Newton mode, scalar formulation (used by the 8-column / affine variant) ---------------------

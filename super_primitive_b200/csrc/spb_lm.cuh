@@ -7,23 +7,29 @@
 
 static __device__ __forceinline__ int tri8(int r, int c) { return r * 8 - r * (r - 1) / 2 + (c - r); }
 
-static __device__ __noinline__ void se3_exp_d(const double* xi, double* T /*3x4 row-major R|t*/) {
+static __device__ __forceinline__ void se3_exp_d(const double* xi, double* T /*3x4 row-major R|t*/) {
     const double tx = xi[0], ty = xi[1], tz = xi[2], px = xi[3], py = xi[4], pz = xi[5];
     const double th2 = px * px + py * py + pz * pz;
     double A, B, C;
     if (th2 < 1e-16) {
         A = 1.0 - th2 / 6.0; B = 0.5 - th2 / 24.0; C = 1.0 / 6.0 - th2 / 120.0;
     } else {
-        const double th = sqrt(th2);
-        A = sin(th) / th; B = (1.0 - cos(th)) / th2; C = (th - sin(th)) / (th2 * th);
+        const double rth = rsqrt(th2), th = th2 * rth, r2 = rth * rth;
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        A = sn * rth; B = (1.0 - cs) * r2; C = (th - sn) * (r2 * rth);
     }
     const double K[9] = {0, -pz, py, pz, 0, -px, -py, px, 0};
     double K2[9];
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 3; ++j) K2[3 * i + j] = K[3 * i] * K[j] + K[3 * i + 1] * K[3 + j] + K[3 * i + 2] * K[6 + j];
     const double tau[3] = {tx, ty, tz};
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
         double vt = 0.0;
+#pragma unroll
         for (int j = 0; j < 3; ++j) {
             const double I = (i == j) ? 1.0 : 0.0;
             T[4 * i + j] = I + A * K[3 * i + j] + B * K2[3 * i + j];
@@ -35,7 +41,8 @@ static __device__ __noinline__ void se3_exp_d(const double* xi, double* T /*3x4 
 
 // body shared by the standalone kernel (k_lm_update) and the fused finalize+solve kernel; any block size that
 // is a multiple of 32 up to SPB_LM_MAXWARPS warps
-#define SPB_LM_MAXWARPS 8
+#define SPB_LM_MAXWARPS 32
+#define SPB_LM_CHUNK 512                         // segments whose 1/D is staged in shared memory per pass
 // gn_pair / gn_seg are deliberately NOT __restrict__: the fused kernel writes them earlier in the same launch, so
 // they must be read with ordinary (coherent) loads, not through the read-only path.
 __device__ __forceinline__ void lm_update_body(const float* gn_pair, const float* gn_seg,
@@ -53,7 +60,9 @@ __device__ __forceinline__ void lm_update_body(const float* gn_pair, const float
     float* pose = poses + (size_t)p * 16;
     __shared__ int s_accept;
     __shared__ float s_lam;
-    __shared__ double s_red[SPB_LM_MAXWARPS][44];
+    __shared__ double s_red[SPB_LM_MAXWARPS / 2][44];          // one row per group of 64 threads
+    __shared__ double s_inv[SPB_LM_CHUNK];
+    __shared__ double s_sys[44];
     __shared__ double s_xi[8];
 
     if (threadIdx.x == 0) {
@@ -89,94 +98,122 @@ __device__ __forceinline__ void lm_update_body(const float* gn_pair, const float
     }
     __syncthreads();
     const float* A = sp + 32;          // saved system (== current one after an accept)
-    // Schur complement accumulation over segments (float64)
-    double loc[44];
-#pragma unroll
-    for (int i = 0; i < 44; ++i) loc[i] = 0.0;
-    for (int b = threadIdx.x; b < n; b += blockDim.x) {
-        const float* sb = ss + (size_t)b * SV_SEG + 2;
-        const double D = (double)sb[8] * (1.0 + lam);
-        if (!(D > 1e-30)) continue;
-        const double inv = 1.0 / D;
-        const double gd = sb[9];
-        int q = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const double bi = (double)sb[i] * inv;
-#pragma unroll
-            for (int j = i; j < 8; ++j) loc[q++] += bi * (double)sb[j];
-            loc[36 + i] += bi * gd;
+    // Schur complement sum over the segments (float64), organised for latency: the CTA is cut into groups of 64
+    // threads; thread q < 44 of a group owns ONE entry of  sum_b B_b D_b^-1 [B_b^T | g_d,b]  and walks the
+    // group's share of the segments (the per-segment record is a broadcast read), so there is no cross-lane
+    // reduction at all; the groups' partial sums meet in shared memory.
+    const int ngroups = blockDim.x >> 6, grp = threadIdx.x >> 6, q = threadIdx.x & 63;
+    {
+        int qi = 0, qj = 0;                                     // q < 36: (i, j) of the triangle; q >= 36: rhs row
+        if (q < 36) {
+            int rem = q;
+            while (rem >= 8 - qi) { rem -= 8 - qi; ++qi; }
+            qj = qi + rem;
+        } else {
+            qi = q - 36; qj = 9;
         }
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-#pragma unroll
-    for (int i = 0; i < 44; ++i) {
-        double v = loc[i];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[warp][i] = v;
+        double accq = 0.0;
+        for (int base = 0; base < n; base += SPB_LM_CHUNK) {
+            const int m = min(SPB_LM_CHUNK, n - base);
+            for (int b = threadIdx.x; b < m; b += blockDim.x) {
+                const double D = (double)ss[(size_t)(base + b) * SV_SEG + 2 + 8] * (1.0 + lam);
+                s_inv[b] = (D > 1e-30) ? 1.0 / D : 0.0;
+            }
+            __syncthreads();
+            if (q < 44 && grp < ngroups) {
+                for (int b = grp; b < m; b += ngroups) {
+                    const float* sb = ss + (size_t)(base + b) * SV_SEG + 2;
+                    accq = fma((double)sb[qi] * s_inv[b], (double)sb[qj], accq);
+                }
+            }
+            __syncthreads();
+        }
+        if (q < 44 && grp < ngroups) s_red[grp][q] = accq;
+        __syncthreads();
+        // entry q of the damped Schur system, still one thread per entry:  S = A + lam diag(A) - sum,  rhs = -(g_p - sum)
+        if (threadIdx.x < 44) {
+            double sub = 0.0;
+            for (int w = 0; w < ngroups; ++w) sub += s_red[w][q];
+            if (q < 36) {
+                const double a = (double)A[q];                  // q enumerates the triangle exactly like tri8(qi, qj)
+                s_sys[q] = (qi == qj) ? fma(lam, a, a) - sub : a - sub;
+            } else {
+                s_sys[q] = -((double)A[SPB_GN_NA + qi] - sub);
+            }
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        // everything below is unrolled with compile-time indices: S, rhs, y, x stay in registers (no local memory)
         double S[8][8], rhs[8];
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
+#pragma unroll
             for (int j = i; j < 8; ++j) {
-                const int q = tri8(i, j);
-                double sub = 0.0;
-                for (int w = 0; w < nwarps; ++w) sub += s_red[w][q];
-                double v = (double)A[q] - sub;
-                if (i == j) v += lam * (double)A[q];
+                const double v = s_sys[tri8(i, j)];
                 S[i][j] = v; S[j][i] = v;
             }
-            double subr = 0.0;
-            for (int w = 0; w < nwarps; ++w) subr += s_red[w][36 + i];
-            rhs[i] = -((double)A[SPB_GN_NA + i] - subr);
+            rhs[i] = s_sys[36 + i];
         }
         const int np = with_affine ? 8 : 6;
-        bool active[8];
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
-            active[i] = (i < np) && (S[i][i] > 1e-30) && isfinite(S[i][i]);
-            if (!active[i]) {
+            const bool active = (i < np) && (S[i][i] > 1e-30) && isfinite(S[i][i]);
+            if (!active) {
+#pragma unroll
                 for (int j = 0; j < 8; ++j) { S[i][j] = 0.0; S[j][i] = 0.0; }
                 S[i][i] = 1.0; rhs[i] = 0.0;
             }
         }
-        // Cholesky S = L L^T (in place, lower), tiny jitter for semi-definite cases
+        // Cholesky S = L L^T (in place, lower); rl[j] = 1 / L[j][j] (one rsqrt per column, no divisions)
         bool ok = true;
-        for (int j = 0; j < 8 && ok; ++j) {
+        double rl[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
             double d = S[j][j];
-            for (int q = 0; q < j; ++q) d -= S[j][q] * S[j][q];
-            if (!(d > 0.0)) { ok = false; break; }
-            const double l = sqrt(d);
-            S[j][j] = l;
+#pragma unroll
+            for (int qq = 0; qq < j; ++qq) d -= S[j][qq] * S[j][qq];
+            if (!(d > 0.0)) { ok = false; d = 1.0; }
+            rl[j] = rsqrt(d);
+            S[j][j] = d * rl[j];
+#pragma unroll
             for (int i = j + 1; i < 8; ++i) {
                 double v = S[i][j];
-                for (int q = 0; q < j; ++q) v -= S[i][q] * S[j][q];
-                S[i][j] = v / l;
+#pragma unroll
+                for (int qq = 0; qq < j; ++qq) v -= S[i][qq] * S[j][qq];
+                S[i][j] = v * rl[j];
             }
         }
-        double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (ok) {
-            double y[8];
-            for (int i = 0; i < 8; ++i) {
-                double v = rhs[i];
-                for (int q = 0; q < i; ++q) v -= S[i][q] * y[q];
-                y[i] = v / S[i][i];
-            }
-            for (int i = 7; i >= 0; --i) {
-                double v = y[i];
-                for (int q = i + 1; q < 8; ++q) v -= S[q][i] * x[q];
-                x[i] = v / S[i][i];
-            }
-        } else {
+        double x[8], y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double v = rhs[i];
+#pragma unroll
+            for (int qq = 0; qq < i; ++qq) v -= S[i][qq] * y[qq];
+            y[i] = v * rl[i];
+        }
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+            double v = y[i];
+#pragma unroll
+            for (int qq = i + 1; qq < 8; ++qq) v -= S[qq][i] * x[qq];
+            x[i] = v * rl[i];
+        }
+        if (!ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = 0.0;
             st[0] = fminf(st[0] * 8.0f, 1e7f);   // not positive definite: damp harder next time
         }
         double nrm = 0.0;
+#pragma unroll
         for (int i = 0; i < 8; ++i) { s_xi[i] = x[i]; nrm += x[i] * x[i]; }
         st[6] = (float)sqrt(nrm);
         // T <- Exp(xi) T_saved
         double E[12];
         se3_exp_d(x, E);
+#pragma unroll
         for (int i = 0; i < 3; ++i) {
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
                 double v = E[4 * i] * (double)sp[j] + E[4 * i + 1] * (double)sp[4 + j] + E[4 * i + 2] * (double)sp[8 + j];
                 if (j == 3) v += E[4 * i + 3];
