@@ -179,6 +179,28 @@ int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_
                         float* out_pair, float* out_gk, void* ev_before, void* ev_after,
                         void* stream);
 
+/* Device-resident first-order iteration (the reference's optimiser, kept on the device): torch.optim.Adam on the
+ * log-depth seeds (odometery/two_frame_sfm.py:117-121), on a twist increment of the pose with the tracker's
+ * bookkeeping (odometery/odometery.py:303-310, 386-403: cost at Exp(delta) T, then T <- Exp(delta) T and delta
+ * re-zeroed, moments kept) and, when with_affine == 1, on the target brightness terms.
+ *   out_pair / out_gk : as written by spb_grad_accumulate
+ *   adam_pair [n_pairs][SPB_ADAM_PAIR] = {step count, m[8], v[8], -} (twist 0..5 = translation, rotation; 6..7 affine)
+ *   adam_seg  [seg_total][SPB_ADAM_SEG] = {m, v};  both zero-initialised by the caller
+ *   lr_pose, lr_k, lr_aff, beta1, beta2, eps : torch.optim.Adam hyper-parameters (float64, as Python holds them)
+ * spb_adam_iterate = spb_grad_accumulate's fused kernel + ONE kernel that reduces the partials and applies the
+ * update (two launches, no host synchronisation, CUDA-graph capturable); with_affine as in spb_gn_accumulate. */
+#define SPB_ADAM_PAIR 24
+#define SPB_ADAM_SEG 2
+int spb_adam_update(const float* out_pair, const float* out_gk, const int32_t* seg_off, const int32_t* seg_cnt,
+                    int n_pairs, int with_affine, float* poses, float* k, float* aff_trg, float* adam_pair,
+                    float* adam_seg, double lr_pose, double lr_k, double lr_aff, double beta1, double beta2,
+                    double eps, void* stream);
+int spb_adam_iterate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, const int32_t* seg_cnt,
+                     int n_pairs, int max_tiles, int with_affine, float* work, int64_t work_stride,
+                     float* out_pair, float* out_gk, float* poses, float* k, float* aff_trg, float* adam_pair,
+                     float* adam_seg, double lr_pose, double lr_k, double lr_aff, double beta1, double beta2,
+                     double eps, void* ev_before, void* ev_after, void* stream);
+
 /* CTAs per pair the batched launches use for (max_tiles, n_pairs): the workspace stride must be
  * >= ctas * nacc + max_tiles * nseg floats (nacc/nseg = 16/1 gradient, 47/10 GN). */
 int spb_gn_ctas(int max_tiles, int n_pairs);

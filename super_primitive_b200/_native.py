@@ -20,6 +20,8 @@ GN_PAIR_NOUT = 48
 GN_SEG_NOUT = 10
 GN_NA = 36
 LM_NSTATE = 8
+ADAM_PAIR = 24
+ADAM_SEG = 2
 MAX_INLINE_PAIRS = 16
 
 
@@ -47,7 +49,7 @@ class SpbStats(C.Structure):
                 ("residual_raw", C.c_void_p), ("trg_ok", C.c_void_p), ("full_mask", C.c_void_p)]
 
 
-_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 _PROTOS = {
     "spb_compact_count": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "spb_compact_scan": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -65,6 +67,9 @@ _PROTOS = {
     "spb_gn_iterate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp]),
     "spb_grad_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "spb_adam_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _d, _d, _vp]),
+    "spb_adam_iterate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d,
+                              _d, _d, _d, _vp, _vp, _vp]),
     "spb_lm_saved_floats": (_i, [_i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
     "spb_lm_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spb_dense_depths": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -364,6 +364,7 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
 #include "spb_fast.cuh"
 #include "spb_gn_packed.cuh"
 #include "spb_lm.cuh"
+#include "spb_adam.cuh"
 
 #ifndef SPB_UNROLL
 #define SPB_UNROLL 1                           // unroll factor of the per-lane point loop
@@ -995,9 +996,11 @@ extern "C" int spb_gn_iterate(const SpbGeom* geoms, const SpbPair* pairs, const 
 }
 
 // gradient mode over device-resident descriptors (batched Adam-parity iterations / benchmark)
-__global__ void k_finalize_grad_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
-                                       const int32_t* __restrict__ seg_off, int ctas, const float* __restrict__ work,
-                                       int64_t work_stride, float* __restrict__ out_pair, float* __restrict__ out_gk) {
+__device__ __forceinline__ void finalize_grad_global_body(const SpbGeom* __restrict__ geoms,
+                                                          const SpbPair* __restrict__ pairs,
+                                                          const int32_t* __restrict__ seg_off, int ctas,
+                                                          const float* __restrict__ work, int64_t work_stride,
+                                                          float* out_pair, float* out_gk) {
     const int pair = blockIdx.x;
     const SpbGeom& g = geoms[pairs[pair].geom];
     const float* pp = work + pair * work_stride;
@@ -1024,6 +1027,25 @@ __global__ void k_finalize_grad_global(const SpbGeom* __restrict__ geoms, const 
     }
 }
 
+__global__ void k_finalize_grad_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
+                                       const int32_t* __restrict__ seg_off, int ctas, const float* __restrict__ work,
+                                       int64_t work_stride, float* __restrict__ out_pair, float* __restrict__ out_gk) {
+    finalize_grad_global_body(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_gk);
+}
+
+// finalize + Adam update + retraction in ONE launch (one CTA per problem): the second kernel of a first-order iteration
+__global__ void __launch_bounds__(256)
+k_grad_finalize_adam(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
+                     const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_cnt, int ctas,
+                     const float* __restrict__ work, int64_t work_stride, float* out_pair, float* out_gk, int with_affine,
+                     const SpbAdamHyper h, float* __restrict__ poses, float* __restrict__ k, float* __restrict__ aff_trg,
+                     float* __restrict__ adam_pair, float* __restrict__ adam_seg) {
+    finalize_grad_global_body(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_gk);
+    __threadfence_block();
+    __syncthreads();
+    adam_update_body(out_pair, out_gk, seg_off, seg_cnt, with_affine, h, poses, k, aff_trg, adam_pair, adam_seg);
+}
+
 extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, int n_pairs,
                                    int max_tiles, int with_affine, float* work, int64_t work_stride, float* out_pair,
                                    float* out_gk, void* ev_before, void* ev_after, void* stream) {
@@ -1047,6 +1069,46 @@ extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, c
     SPB_CHECK_LAUNCH();
     if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
     k_finalize_grad_global<<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_gk);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+static inline bool adam_hyper_ok(double lr_pose, double lr_k, double lr_aff, double beta1, double beta2, double eps) {
+    return lr_pose >= 0.0 && lr_k >= 0.0 && lr_aff >= 0.0 && beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 &&
+           eps >= 0.0;
+}
+
+// One complete first-order iteration in two launches: fused residual+gradient kernel, then finalize + Adam update +
+// retraction (k_grad_finalize_adam).
+extern "C" int spb_adam_iterate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, const int32_t* seg_cnt,
+                                int n_pairs, int max_tiles, int with_affine, float* work, int64_t work_stride,
+                                float* out_pair, float* out_gk, float* poses, float* k, float* aff_trg, float* adam_pair,
+                                float* adam_seg, double lr_pose, double lr_k, double lr_aff, double beta1, double beta2,
+                                double eps, void* ev_before, void* ev_after, void* stream) {
+    if (!geoms || !pairs || !seg_off || !seg_cnt || n_pairs < 1 || max_tiles < 1 || !work || !out_pair || !out_gk ||
+        !poses || !k || !adam_pair || !adam_seg || !adam_hyper_ok(lr_pose, lr_k, lr_aff, beta1, beta2, eps))
+        return SPB_EINVAL;
+    if (with_affine == 1 && !aff_trg) return SPB_EINVAL;
+    if (n_pairs > 65535) return SPB_ELIMIT;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = ctas_grad(max_tiles, n_pairs);
+    if (work_stride < (int64_t)ctas * SPB_PAIR_NOUT + max_tiles) return SPB_EINVAL;
+    dim3 grid(ctas, n_pairs);
+    if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
+    if (with_affine) {
+        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GRAD, 6, true>);
+        if (e != cudaSuccess) return (int)e;
+        k_align_global<MODE_GRAD, 6, true><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
+    } else {
+        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GRAD, 6, false>);
+        if (e != cudaSuccess) return (int)e;
+        k_align_global<MODE_GRAD, 6, false><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
+    }
+    SPB_CHECK_LAUNCH();
+    if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
+    const SpbAdamHyper h{lr_pose, lr_k, lr_aff, beta1, beta2, eps};
+    k_grad_finalize_adam<<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, seg_cnt, ctas, work, work_stride, out_pair, out_gk,
+                                                  with_affine == 1 ? 1 : 0, h, poses, k, aff_trg, adam_pair, adam_seg);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

@@ -168,6 +168,63 @@ class AlignmentBatch:
                                                 self.out_gk.data_ptr(), e0, e1, _stream()), "spb_grad_accumulate")
         self.launches += 2
 
+    def _adam_buffers(self):
+        if getattr(self, "adam_pair", None) is None:
+            self.adam_pair = torch.zeros((self.n, nat.ADAM_PAIR), dtype=torch.float32, device=self.device)
+            self.adam_seg = torch.zeros((self.seg_total, nat.ADAM_SEG), dtype=torch.float32, device=self.device)
+
+    def adam_step(self, ev=None, lr_pose=1e-2, lr_k=1e-3, lr_aff=5e-3, betas=(0.9, 0.999), eps=1e-8):
+        """One first-order iteration for every problem in two launches (``spb_adam_iterate``): the fused
+        residual+gradient kernel, then finalize + torch.optim.Adam update of (twist increment, log-depth seeds,
+        target affine when ``with_affine``) + retraction ``T <- Exp(delta) T`` -- the reference's optimiser
+        (odometery/two_frame_sfm.py:117-121 learning rates; tracker bookkeeping odometery/odometery.py:386-403)
+        kept on the device, no host synchronisation."""
+        self._adam_buffers()
+        e0, e1 = (None, None) if ev is None else (ev[0].cuda_event, ev[1].cuda_event)
+        nat.check(nat.lib().spb_adam_iterate(self.d_geoms.data_ptr(), self.d_pairs.data_ptr(), self.d_seg_off.data_ptr(),
+                                             self.d_seg_cnt.data_ptr(), self.n, self.max_tiles,
+                                             1 if self.with_affine else (2 if self.use_affine else 0),
+                                             self.work.data_ptr(), self.work_stride, self.out_pair.data_ptr(),
+                                             self.out_gk.data_ptr(), self.poses.data_ptr(), self.k.data_ptr(),
+                                             self.aff_trg.data_ptr() if self.with_affine else None,
+                                             self.adam_pair.data_ptr(), self.adam_seg.data_ptr(), float(lr_pose),
+                                             float(lr_k), float(lr_aff), float(betas[0]), float(betas[1]), float(eps),
+                                             e0, e1, _stream()), "spb_adam_iterate")
+        self.launches += 2
+
+    def adam_update(self, lr_pose=1e-2, lr_k=1e-3, lr_aff=5e-3, betas=(0.9, 0.999), eps=1e-8):
+        """The update alone, from the gradients ``grad_step`` left in ``out_pair`` / ``out_gk``."""
+        self._adam_buffers()
+        nat.check(nat.lib().spb_adam_update(self.out_pair.data_ptr(), self.out_gk.data_ptr(), self.d_seg_off.data_ptr(),
+                                            self.d_seg_cnt.data_ptr(), self.n, 1 if self.with_affine else 0,
+                                            self.poses.data_ptr(), self.k.data_ptr(),
+                                            self.aff_trg.data_ptr() if self.with_affine else None,
+                                            self.adam_pair.data_ptr(), self.adam_seg.data_ptr(), float(lr_pose),
+                                            float(lr_k), float(lr_aff), float(betas[0]), float(betas[1]), float(eps),
+                                            _stream()), "spb_adam_update")
+        self.launches += 1
+
+    def run_adam(self, iters, **kw):
+        for _ in range(iters):
+            self.adam_step(**kw)
+
+    def capture_adam(self, iters, **kw):
+        """CUDA-graph ``iters`` first-order iterations. Returns the graph."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.adam_step(**kw)    # warm-up outside capture
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(iters):
+                self.adam_step(**kw)
+        return graph
+
+    def grad_costs(self):
+        """mean |r| per problem at the parameters of the last gradient evaluation (grad_step / adam_step)."""
+        return self.out_pair[:, 0]
+
     def run_gn(self, iters):
         for _ in range(iters):
             self.gn_step()
