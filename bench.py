@@ -335,6 +335,36 @@ def time_dropin_single_pair(device, iters=60, warm=10):
                     "= 1 host sync, Adam.step); host/launch-bound"}
 
 
+def time_device_loop_single_pair(device, iters=200):
+    """ONE C2 pair (the shape of real-time use: nothing to batch over) through the device-resident loops: each
+    iteration is two launches with no host synchronisation; eager and replayed from a CUDA graph."""
+    batch, _ = build_batch(1, device, seed0=7)
+    out = {}
+    for name, run, cap in (("gn", batch.run_gn, batch.capture_gn), ("adam", batch.run_adam, batch.capture_adam)):
+        run(20)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run(iters)
+        b.record()
+        torch.cuda.synchronize()
+        eager_ms = a.elapsed_time(b) / iters
+        graph = cap(50)
+        graph.replay()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(4):
+            graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        graph_ms = a.elapsed_time(b) / 200
+        out[name] = {"eager_us_per_iter": 1e3 * eager_ms, "graph_us_per_iter": 1e3 * graph_ms,
+                     "iters_per_s": 1e3 / min(eager_ms, graph_ms)}
+    out["what"] = ("device-resident GN/LM and Adam loops on ONE 640x480 / 64-segment pair (two launches per iteration, "
+                   "no host sync): latency-bound, the real-time tracking shape")
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -456,9 +486,10 @@ def main():
 
     # ---- drop-in arm: the reference's own loop (photomeric_cost -> backward -> Adam.step) through the public
     #      Python surface, ONE pair, device-resident inputs: launch/host-bound, reported for context -------------
-    dropin = None
+    dropin = device_loop = None
     if rank == 0 and not args.no_e2e:
         dropin = time_dropin_single_pair(device)
+        device_loop = time_device_loop_single_pair(device)
 
     # ---- the only collective of the path: final gather of poses / seeds / cost -------------------------
     gather_ms = None
@@ -518,6 +549,7 @@ def main():
             "kernel_ms": other_kern_ms, "roofline_frac": o_bytes / (other_kern_ms * 1e-3) / 1e9 / peak}
         if dropin is not None:
             line["dropin_single_pair"] = dropin
+            line["device_loop_single_pair"] = device_loop
         if gather_ms is not None:
             line["final_gather_ms"] = gather_ms
         print(json.dumps(line), flush=True)

@@ -578,6 +578,41 @@ k_align_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pa
     align_body_warp<MODE, NP, AFF>(s_g, s_pr, irls_eps, base, base + (size_t)gridDim.x * NACC);
 }
 
+// Fixed-order sum over the per-CTA partials [ctas][NACC] (contiguous): the block's threads form R = blockDim / NACC
+// row groups; thread (r, c) adds rows r, r + R, ... of column c (consecutive threads read consecutive floats, 8 loads
+// in flight), the groups meet in shared memory and thread c < NACC adds them in group order.  Returns the total to
+// threads < NACC (0 elsewhere).  A serial loop over several hundred CTAs costs tens of microseconds when one
+// problem owns the whole GPU.  Needs blockDim >= NACC; contains two __syncthreads().
+#define SPB_FIN_SMEM 1024
+template <int NACC>
+__device__ __forceinline__ float sum_cta_partials(const float* pp, int ctas, float* s_part /* [SPB_FIN_SMEM] */) {
+    const int R = min((int)blockDim.x, SPB_FIN_SMEM) / NACC;
+    const int r = threadIdx.x / NACC, c = threadIdx.x - r * NACC;
+    float v = 0.f;
+    if (r < R) {
+        constexpr int U = 8;
+        for (int row0 = r; row0 < ctas; row0 += U * R) {
+            float b[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int row = row0 + u * R;
+                b[u] = (row < ctas) ? pp[(size_t)row * NACC + c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) v += b[u];
+        }
+        s_part[r * NACC + c] = v;
+    }
+    __syncthreads();
+    float tot = 0.f;
+    if (threadIdx.x < NACC) {
+        const int groups = min(R, ctas);
+        for (int q = 0; q < groups; ++q) tot += s_part[q * NACC + threadIdx.x];
+    }
+    __syncthreads();
+    return tot;
+}
+
 // Fixed-order sum of the per-tile partials of TWO segments at once (tiles [ta0,ta1) and [tb0,tb1), NSEG floats per
 // tile, contiguous).  Lanes walk the contiguous float range coalesced: lane l < G*NSEG always meets value l % NSEG
 // (G = 32 / NSEG tiles per round), so one register per segment accumulates; the G lanes holding the same value
@@ -643,10 +678,11 @@ __global__ void k_finalize_grad(const __grid_constant__ SpbGeom g, const __grid_
     const float* ps = pp + (size_t)ctas * SPB_PAIR_NOUT;
     const float norm = 1.0f / (3.0f * (float)g.n_pts);
     __shared__ float s_v[SPB_PAIR_NOUT];
+    __shared__ float s_part[SPB_FIN_SMEM];
     bool finite = true;
+    const float tot = sum_cta_partials<SPB_PAIR_NOUT>(pp, ctas, s_part);
     if (threadIdx.x < SPB_PAIR_NOUT) {
-        float v = 0.f;
-        for (int cta = 0; cta < ctas; ++cta) v += pp[(size_t)cta * SPB_PAIR_NOUT + threadIdx.x];
+        float v = tot;
         v *= grad_col_scale(threadIdx.x, g.K, scale_cols != 0);
         v = (threadIdx.x == 15) ? v : v * norm;
         out_pair[pair * SPB_PAIR_NOUT + threadIdx.x] = v;
@@ -692,9 +728,10 @@ __device__ __forceinline__ void finalize_gn_body(const SpbGeom* __restrict__ geo
     const float* pp = work + pair * work_stride;
     const float* ps = pp + (size_t)ctas * NACC;
     float* op = out_pair + (size_t)pair * SPB_GN_PAIR_NOUT;
+    __shared__ float s_part[SPB_FIN_SMEM];
+    const float tot = sum_cta_partials<NACC>(pp, ctas, s_part);
     if (threadIdx.x < NACC) {
-        float v = 0.f;
-        for (int cta = 0; cta < ctas; ++cta) v += pp[(size_t)cta * NACC + threadIdx.x];
+        const float v = tot;
         // scatter into the fixed 8-column layout
         const int i = threadIdx.x;
         if (NP == 8) {
@@ -811,9 +848,10 @@ k_align_points(const float* __restrict__ src_pts, const float* __restrict__ src_
 }
 
 __global__ void k_finalize_points(int ctas, int P, const float* __restrict__ work, float* __restrict__ out_pair) {
+    __shared__ float s_part[SPB_FIN_SMEM];
+    const float tot = sum_cta_partials<SPB_PAIR_NOUT>(work, ctas, s_part);
     if (threadIdx.x < SPB_PAIR_NOUT) {
-        float v = 0.f;
-        for (int cta = 0; cta < ctas; ++cta) v += work[(size_t)cta * SPB_PAIR_NOUT + threadIdx.x];
+        const float v = tot;
         const float norm = 1.0f / (3.0f * (float)P);
         out_pair[threadIdx.x] = (threadIdx.x == 15) ? v : v * norm;
     }
@@ -909,7 +947,7 @@ extern "C" int spb_cost_grad_points(const float* src_pts, const float* src_px, c
     const int ctas = ctas_for_points(P);
     k_align_points<<<ctas, SPB_THREADS, 0, st>>>(src_pts, src_px, src_ok, P, H, W, *pair, work);
     SPB_CHECK_LAUNCH();
-    k_finalize_points<<<1, 32, 0, st>>>(ctas, P, work, out_pair);
+    k_finalize_points<<<1, 256, 0, st>>>(ctas, P, work, out_pair);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
@@ -1006,9 +1044,10 @@ __device__ __forceinline__ void finalize_grad_global_body(const SpbGeom* __restr
     const float* pp = work + pair * work_stride;
     const float* ps = pp + (size_t)ctas * SPB_PAIR_NOUT;
     const float norm = 1.0f / (3.0f * (float)g.n_pts);
+    __shared__ float s_part[SPB_FIN_SMEM];
+    const float tot = sum_cta_partials<SPB_PAIR_NOUT>(pp, ctas, s_part);
     if (threadIdx.x < SPB_PAIR_NOUT) {
-        float v = 0.f;
-        for (int cta = 0; cta < ctas; ++cta) v += pp[(size_t)cta * SPB_PAIR_NOUT + threadIdx.x];
+        float v = tot;
         v *= grad_col_scale(threadIdx.x, g.K, true);
         out_pair[pair * SPB_PAIR_NOUT + threadIdx.x] = (threadIdx.x == 15) ? v : v * norm;
     }

@@ -153,7 +153,7 @@ class _PairCost(torch.autograd.Function):
             # the reference asserts finiteness at five sites per call (core/dense_optim.py:44,78,311,321,340-343);
             # here the finalize kernel folds outputs AND inputs (log-depth seeds, pose) into one flag per pair and
             # a single device->host read covers the call.  (A NaN seed would otherwise just invalidate its points.)
-            if float(out_flag.min()) < 0.5:
+            if float(out_flag if B == 1 else out_flag.min()) < 0.5:
                 raise AssertionError("non-finite photometric cost, gradient or input (log-depth / pose)")
         ctx.save_for_backward(out_pair, out_gk, out_pose)
         ctx.shapes = (None if aff_src is None else aff_src.shape, None if aff_trg is None else aff_trg.shape,
@@ -164,13 +164,15 @@ class _PairCost(torch.autograd.Function):
     def backward(ctx, g):
         out_pair, out_gk, out_pose = ctx.saved_tensors
         B = out_pair.shape[0]
-        g = g.reshape(B).to(torch.float32)
+        g = g.reshape(B)
+        if g.dtype != torch.float32:
+            g = g.to(torch.float32)
         needs = ctx.needs_input_grad
         g_k = g_pose = g_as = g_at = None
         if needs[0]:
-            g_k = out_gk[0] * g[0] if B == 1 else (g[:, None] * out_gk).sum(0)
+            g_k = out_gk[0] * g if B == 1 else (g[:, None] * out_gk).sum(0)     # (N,) * (1,) broadcasts: one kernel
         if needs[1]:
-            g_pose = (out_pose * g[:, None, None]).reshape(ctx.shapes[2])
+            g_pose = (out_pose * (g if B == 1 else g[:, None, None])).reshape(ctx.shapes[2])
         s_shape, t_shape, _ = ctx.shapes
         if s_shape is not None and (needs[2] or needs[3]):
             ga = out_pair[:, 13:15] * g[:, None]
