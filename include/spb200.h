@@ -167,7 +167,7 @@ int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t*
  * kernel that reduces the partials (into gn_pair / gn_seg), solves the damped system and retracts (what
  * spb_gn_accumulate + spb_lm_update do in three).  Arguments as in those two functions. */
 int spb_gn_iterate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, const int32_t* seg_cnt,
-                   int n_pairs, int max_tiles, float irls_eps, int with_affine, float* work,
+                   int n_pairs, int max_tiles, float irls_eps, int with_affine, int hold_depth, float* work,
                    int64_t work_stride, float* gn_pair, float* gn_seg, float* poses, float* k, float* aff_trg,
                    float* lm_state, float* saved_pair, float* saved_seg, void* ev_before, void* ev_after,
                    void* stream);
@@ -210,11 +210,13 @@ int spb_gn_ctas(int max_tiles, int n_pairs);
  *   lm_state [n_pairs][SPB_LM_NSTATE] = {lambda, accepted cost, initialised, n_accept, n_reject,
  *                                        last cost, |step|, -}
  *   saved_*  : last accepted parameters + system (sizes from spb_lm_saved_floats)
- * poses [n_pairs][16], k[seg_total] and aff_trg [n_pairs][2] (may be NULL) are updated in place. */
+ * poses [n_pairs][16], k[seg_total] and aff_trg [n_pairs][2] (may be NULL) are updated in place.
+ * hold_depth != 0: the log-depth seeds are held (no elimination, dk = 0) and only the pose (+ affine) moves -- the
+ * reference's tracker optimises exactly that set (odometery/odometery.py:303-310). */
 #define SPB_LM_NSTATE 8
 int spb_lm_saved_floats(int n_pairs, int seg_total, int64_t* pair_floats, int64_t* seg_floats);
 int spb_lm_update(const float* gn_pair, const float* gn_seg, const int32_t* seg_off,
-                  const int32_t* seg_cnt, int n_pairs, int with_affine, float* poses, float* k,
+                  const int32_t* seg_cnt, int n_pairs, int with_affine, int hold_depth, float* poses, float* k,
                   float* aff_trg, float* lm_state, float* saved_pair, float* saved_seg, void* stream);
 
 /* ================================== geometry-only entry points ================================ */

@@ -64,14 +64,14 @@ _PROTOS = {
     "spb_workspace_floats_points": (_i64, [_i]),
     "spb_gn_ctas": (_i, [_i, _i]),
     "spb_gn_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "spb_gn_iterate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+    "spb_gn_iterate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp]),
     "spb_grad_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "spb_adam_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _d, _d, _vp]),
     "spb_adam_iterate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d,
                               _d, _d, _d, _vp, _vp, _vp]),
     "spb_lm_saved_floats": (_i, [_i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
-    "spb_lm_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spb_lm_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spb_dense_depths": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "spb_depth_splat": (_i, [C.POINTER(SpbGeom), _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "spb_depth_splat_points": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

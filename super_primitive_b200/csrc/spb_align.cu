@@ -804,13 +804,14 @@ __global__ void __launch_bounds__(SPB_FIN_THREADS)
 k_gn_finalize_solve(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
                     const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_cnt, int ctas,
                     const float* __restrict__ work, int64_t work_stride, float* gn_pair, float* gn_seg,
-                    int with_affine, float* __restrict__ poses, float* __restrict__ k,
+                    int with_affine, int hold_depth, float* __restrict__ poses, float* __restrict__ k,
                     float* __restrict__ aff_trg, float* __restrict__ lm_state, float* __restrict__ saved_pair,
                     float* __restrict__ saved_seg) {
     finalize_gn_body<NP>(geoms, pairs, seg_off, ctas, work, work_stride, gn_pair, gn_seg);
     __threadfence_block();
     __syncthreads();
-    lm_update_body(gn_pair, gn_seg, seg_off, seg_cnt, with_affine, poses, k, aff_trg, lm_state, saved_pair, saved_seg);
+    lm_update_body(gn_pair, gn_seg, seg_off, seg_cnt, with_affine, hold_depth, poses, k, aff_trg, lm_state, saved_pair,
+                   saved_seg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1005,7 +1006,7 @@ extern "C" int spb_gn_accumulate(const SpbGeom* geoms, const SpbPair* pairs, con
 // One complete GN/LM iteration in two launches: fused residual+Jacobian+normal-equation kernel, then
 // finalize + damped solve + retraction (k_gn_finalize_solve).
 extern "C" int spb_gn_iterate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, const int32_t* seg_cnt,
-                              int n_pairs, int max_tiles, float irls_eps, int with_affine, float* work,
+                              int n_pairs, int max_tiles, float irls_eps, int with_affine, int hold_depth, float* work,
                               int64_t work_stride, float* gn_pair, float* gn_seg, float* poses, float* k,
                               float* aff_trg, float* lm_state, float* saved_pair, float* saved_seg, void* ev_before,
                               void* ev_after, void* stream) {
@@ -1023,12 +1024,12 @@ extern "C" int spb_gn_iterate(const SpbGeom* geoms, const SpbPair* pairs, const 
     const int opt_aff = with_affine == 1 ? 1 : 0;
     if (with_affine == 1)
         k_gn_finalize_solve<8><<<n_pairs, SPB_FIN_THREADS, 0, st>>>(geoms, pairs, seg_off, seg_cnt, ctas, work, work_stride, gn_pair,
-                                                        gn_seg, opt_aff, poses, k, aff_trg, lm_state, saved_pair,
-                                                        saved_seg);
+                                                        gn_seg, opt_aff, hold_depth ? 1 : 0, poses, k, aff_trg, lm_state,
+                                                        saved_pair, saved_seg);
     else
         k_gn_finalize_solve<6><<<n_pairs, SPB_FIN_THREADS, 0, st>>>(geoms, pairs, seg_off, seg_cnt, ctas, work, work_stride, gn_pair,
-                                                        gn_seg, opt_aff, poses, k, aff_trg, lm_state, saved_pair,
-                                                        saved_seg);
+                                                        gn_seg, opt_aff, hold_depth ? 1 : 0, poses, k, aff_trg, lm_state,
+                                                        saved_pair, saved_seg);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

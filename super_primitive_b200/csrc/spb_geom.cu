@@ -543,4 +543,4 @@ extern "C" int spb_depth_splat_points(const float* pts, int P, const float* K, i
 
 extern "C" int spb_tile_points(void) { return SPB_TILE; }
 
-extern "C" int spb_version(void) { return 103; }
+extern "C" int spb_version(void) { return 104; }

@@ -47,7 +47,8 @@ static __device__ __forceinline__ void se3_exp_d(const double* xi, double* T /*3
 // they must be read with ordinary (coherent) loads, not through the read-only path.
 __device__ __forceinline__ void lm_update_body(const float* gn_pair, const float* gn_seg,
                                                const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_cnt,
-                                               int with_affine, float* __restrict__ poses, float* __restrict__ k,
+                                               int with_affine, int hold_depth, float* __restrict__ poses,
+                                               float* __restrict__ k,
                                                float* __restrict__ aff_trg, float* __restrict__ lm_state,
                                                float* __restrict__ saved_pair, float* __restrict__ saved_seg) {
     const int p = blockIdx.x;
@@ -117,7 +118,7 @@ __device__ __forceinline__ void lm_update_body(const float* gn_pair, const float
             const int m = min(SPB_LM_CHUNK, n - base);
             for (int b = threadIdx.x; b < m; b += blockDim.x) {
                 const double D = (double)ss[(size_t)(base + b) * SV_SEG + 2 + 8] * (1.0 + lam);
-                s_inv[b] = (D > 1e-30) ? 1.0 / D : 0.0;
+                s_inv[b] = (D > 1e-30 && !hold_depth) ? 1.0 / D : 0.0;   // held seeds: no elimination, S = damped A
             }
             __syncthreads();
             if (q < 44 && grp < ngroups) {
@@ -231,7 +232,7 @@ __device__ __forceinline__ void lm_update_body(const float* gn_pair, const float
         const float* sb = ss + (size_t)b * SV_SEG + 2;
         const double D = (double)sb[8] * (1.0 + lam);
         double dk = 0.0;
-        if (D > 1e-30) {
+        if (D > 1e-30 && !hold_depth) {
             double v = sb[9];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v += (double)sb[i] * s_xi[i];

@@ -12,10 +12,11 @@
 
 __global__ void __launch_bounds__(128)
 k_lm_update(const float* __restrict__ gn_pair, const float* __restrict__ gn_seg, const int32_t* __restrict__ seg_off,
-            const int32_t* __restrict__ seg_cnt, int with_affine, float* __restrict__ poses, float* __restrict__ k,
-            float* __restrict__ aff_trg, float* __restrict__ lm_state, float* __restrict__ saved_pair,
-            float* __restrict__ saved_seg) {
-    lm_update_body(gn_pair, gn_seg, seg_off, seg_cnt, with_affine, poses, k, aff_trg, lm_state, saved_pair, saved_seg);
+            const int32_t* __restrict__ seg_cnt, int with_affine, int hold_depth, float* __restrict__ poses,
+            float* __restrict__ k, float* __restrict__ aff_trg, float* __restrict__ lm_state,
+            float* __restrict__ saved_pair, float* __restrict__ saved_seg) {
+    lm_update_body(gn_pair, gn_seg, seg_off, seg_cnt, with_affine, hold_depth, poses, k, aff_trg, lm_state, saved_pair,
+                   saved_seg);
 }
 
 extern "C" int spb_lm_saved_floats(int n_pairs, int seg_total, int64_t* pair_floats, int64_t* seg_floats) {
@@ -26,13 +27,15 @@ extern "C" int spb_lm_saved_floats(int n_pairs, int seg_total, int64_t* pair_flo
 }
 
 extern "C" int spb_lm_update(const float* gn_pair, const float* gn_seg, const int32_t* seg_off,
-                             const int32_t* seg_cnt, int n_pairs, int with_affine, float* poses, float* k,
-                             float* aff_trg, float* lm_state, float* saved_pair, float* saved_seg, void* stream) {
+                             const int32_t* seg_cnt, int n_pairs, int with_affine, int hold_depth, float* poses,
+                             float* k, float* aff_trg, float* lm_state, float* saved_pair, float* saved_seg,
+                             void* stream) {
     if (!gn_pair || !gn_seg || !seg_off || !seg_cnt || n_pairs < 1 || !poses || !k || !lm_state || !saved_pair ||
         !saved_seg)
         return SPB_EINVAL;
-    k_lm_update<<<n_pairs, 128, 0, (cudaStream_t)stream>>>(gn_pair, gn_seg, seg_off, seg_cnt, with_affine, poses, k,
-                                                          aff_trg, lm_state, saved_pair, saved_seg);
+    k_lm_update<<<n_pairs, 128, 0, (cudaStream_t)stream>>>(gn_pair, gn_seg, seg_off, seg_cnt, with_affine,
+                                                          hold_depth ? 1 : 0, poses, k, aff_trg, lm_state, saved_pair,
+                                                          saved_seg);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

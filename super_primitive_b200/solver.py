@@ -44,7 +44,7 @@ class AlignmentBatch:
         tau       optional front-of-camera threshold (default 1e-7)
     """
 
-    def __init__(self, problems, with_affine=False, irls_eps=1e-3, lam0=1e-3):
+    def __init__(self, problems, with_affine=False, irls_eps=1e-3, lam0=1e-3, hold_depth=False):
         lib = nat.lib()
         self.n = n = len(problems)
         if n < 1:
@@ -52,6 +52,9 @@ class AlignmentBatch:
         dev = problems[0]['trg_rgba'].device
         self.device = dev
         self.with_affine = bool(with_affine)
+        # hold_depth: the GN/LM loop moves only the pose (+ target affine); the log-depth seeds stay (the reference's
+        # tracker, odometery/odometery.py:303-310).  For the Adam loop pass lr_k=0.
+        self.hold_depth = bool(hold_depth)
         self.irls_eps = float(irls_eps)
         # unique geometries
         geoms, gidx = [], []
@@ -137,6 +140,7 @@ class AlignmentBatch:
     def lm_update(self):
         nat.check(nat.lib().spb_lm_update(self.gn_pair.data_ptr(), self.gn_seg.data_ptr(), self.d_seg_off.data_ptr(),
                                           self.d_seg_cnt.data_ptr(), self.n, 1 if self.with_affine else 0,
+                                          1 if self.hold_depth else 0,
                                           self.poses.data_ptr(), self.k.data_ptr(),
                                           self.aff_trg.data_ptr() if self.with_affine else None,
                                           self.lm_state.data_ptr(), self.saved_pair.data_ptr(),
@@ -150,6 +154,7 @@ class AlignmentBatch:
         nat.check(nat.lib().spb_gn_iterate(self.d_geoms.data_ptr(), self.d_pairs.data_ptr(), self.d_seg_off.data_ptr(),
                                            self.d_seg_cnt.data_ptr(), self.n, self.max_tiles, self.irls_eps,
                                            1 if self.with_affine else (2 if self.use_affine else 0),
+                                           1 if self.hold_depth else 0,
                                            self.work.data_ptr(), self.work_stride, self.gn_pair.data_ptr(),
                                            self.gn_seg.data_ptr(), self.poses.data_ptr(), self.k.data_ptr(),
                                            self.aff_trg.data_ptr() if self.with_affine else None,

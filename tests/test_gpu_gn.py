@@ -153,3 +153,46 @@ def test_gn_recovers_pose_of_a_consistent_planar_scene():
     scale = np.exp(float(batch.k.mean()) - float(k_true.mean()))          # joint scale gauge of (t, depth)
     t_est = T[:3, 3] / scale
     assert np.linalg.norm(t_est - to_np(T_true)[:3, 3]) < 0.15 * np.linalg.norm(to_np(T_true)[:3, 3]), (t_est, scale)
+
+
+def test_pose_only_lm_holds_the_seeds_and_matches_the_reduced_system():
+    """hold_depth: the tracker's parameter set (pose only).  One LM step must equal the solve of the damped pose
+    block alone (no Schur elimination), the seeds must not move, and the loop must still reduce the cost."""
+    from super_primitive_b200 import synthetic as syn
+    from super_primitive_b200.solver import AlignmentBatch, make_problem
+    g = Golden("tiny_rects", "cuda")
+    lvl = g.n_levels - 1
+    src = g.src(lvl)
+    prob = make_problem(src, g.trg(lvl, 0).image, g.trg(lvl, 0).K, g.poses()[0], g.k())
+    batch = AlignmentBatch([prob], hold_depth=True)
+    k0 = to_np(batch.k).copy()
+    T0 = to_np(batch.poses_matrix()[0]).astype(np.float64)
+    batch.gn_step()
+    torch.cuda.synchronize()
+    geo = cf.compact_geometry(g.z["src_regions"], g.z["src_logdepth"], g.z["src_keypoints"])
+    r = cf.evaluate(geo, g.z[f"L{lvl}_src_image"], g.z[f"L{lvl}_trg_images"][0], g.z["src_K"], g.z["src_K"],
+                    g.z["k"], g.z["poses"][0], None, want_gn=True, irls_eps=1e-3)
+    lam = 1e-3
+    A = r["A"] + lam * np.diag(np.diag(r["A"]))
+    xi = np.linalg.solve(A, -r["g_p"])
+    assert np.array_equal(to_np(batch.k), k0), "held seeds moved"
+    assert_close(to_np(batch.poses_matrix()[0]), cf.se3_exp(xi) @ T0, 1e-5, "pose after one pose-only LM step")
+    # consistent scene, true depth: pose-only tracking must recover the pose
+    H, W, N = 120, 160, 8
+    T_true = syn.small_pose(0.03, -0.02, 0.01, 0.010, -0.015, 0.020)
+    s2, t2, k_true = syn.planar_scene_pair(H, W, N, T_true, z0=2.0, kind="strips")
+    s2, t2 = s2.to("cuda"), t2.to("cuda")
+    b2 = AlignmentBatch([make_problem(s2, t2.image, t2.K, torch.eye(4).cuda(), k_true.cuda())], hold_depth=True)
+    b2.gn_accumulate()
+    c0 = float(b2.costs()[0])
+    b2.run_gn(40)
+    torch.cuda.synchronize()
+    c1 = float(b2.lm_state[0, 1]) / (3 * float(b2.pts_per_problem[0]))
+    assert c1 < 0.1 * c0, (c0, c1)
+    assert torch.equal(b2.k.cpu(), k_true.to(torch.float32))
+    T = to_np(b2.poses_matrix()[0]).astype(np.float64)
+    Rerr = T[:3, :3] @ to_np(T_true)[:3, :3].T.astype(np.float64)
+    ang = np.arccos(np.clip((np.trace(Rerr) - 1) / 2, -1, 1))
+    assert ang < 3e-3, f"rotation error {ang:.2e} rad"
+    t_true = to_np(T_true)[:3, 3]
+    assert np.linalg.norm(T[:3, 3] - t_true) < 0.15 * np.linalg.norm(t_true), T[:3, 3]     # depth known: no gauge
