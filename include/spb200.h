@@ -201,6 +201,68 @@ int spb_adam_iterate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* 
                      float* adam_seg, double lr_pose, double lr_k, double lr_aff, double beta1, double beta2,
                      double eps, void* ev_before, void* ev_after, void* stream);
 
+/* ================== coupled problems: the mapping window (odometery/odometery.py:687-915) ================== */
+
+/* The reference's windowed mapping optimises, with ONE torch.optim.Adam, the poses of the frames of a window
+ * (keyframes + supporting frames), the log-depth seeds of its keyframes and the frames' brightness terms over
+ *     loss = sum_{src keyframe s} mean_{b in targets(s)} cost(s -> b)                      (:845-851)
+ * where cost(s -> b) is photomeric_cost_batch evaluated at the relative pose
+ *     Delta_b inv(T_b) T_s inv(Delta_s)                                                    (:793,:817)
+ * of camera-to-world poses T and per-frame twist increments Delta = Exp(delta) held at zero: after optim.step()
+ * every increment is folded in (T_f <- T_f inv(Delta_f)), the pose is re-normalised through a quaternion round trip
+ * (lie/lie_algebra.py:41-48) and delta is re-zeroed while its Adam moments persist (:861-882).  A frame is the
+ * target of several sources (supporting frames serve source s and s+1, :798-800), so its pose / affine gradient is
+ * a sum over edges, and a keyframe's seed gradient is a sum over its outgoing edges -- the coupling SURVEY 8(e)
+ * names.  Here an EDGE (s -> b) is one SpbPair of the batched gradient launch (spb_grad_accumulate) whose `pose`
+ * points into edge_pose, `k` into the source frame's seeds and aff_src / aff_trg into frame_aff; the kernel behind
+ * spb_window_update turns the per-edge gradients into the per-frame Adam update and rewrites the edge poses, so a
+ * whole mapping run stays on the device (no loss.item(), no host-side 4x4 products; CUDA-graph capturable).
+ * All arrays are DEVICE memory; frames and edges of window w are the index ranges win_frame_off[w..w+1],
+ * win_edge_off[w..w+1]; edge_src / edge_trg are global frame indices inside the edge's own window. */
+#define SPB_WIN_OPT_POSE 1      /* frame_flags bits */
+#define SPB_WIN_OPT_AFF 2
+#define SPB_WIN_OPT_SEEDS 4
+#define SPB_WIN_ADAM_FRAME 16   /* per frame: m[8], v[8] (twist 0..5 = translation, rotation; 6..7 = affine a, b) */
+#define SPB_WIN_NSTATE 8        /* per window: {step count, loss, previous loss, converged, -, -, -, -} */
+typedef struct SpbWindow {
+    int32_t n_windows, n_frames, n_edges, seg_total;
+    const int32_t* win_frame_off;   /* [n_windows+1] */
+    const int32_t* win_edge_off;    /* [n_windows+1] */
+    const int32_t* edge_src;        /* [n_edges] source keyframe (global frame index) */
+    const int32_t* edge_trg;        /* [n_edges] target frame */
+    const float*   edge_w;          /* [n_edges] weight of cost_e in the loss = 1 / #targets of its source */
+    const int32_t* edge_seg_off;    /* [n_edges] where spb_grad_accumulate wrote d cost_e / d k (its seg_off) */
+    const int32_t* frame_seg_off;   /* [n_frames] offset of a keyframe's seeds in k */
+    const int32_t* frame_seg_cnt;   /* [n_frames] number of segments (0: not a source) */
+    const uint8_t* frame_flags;     /* [n_frames] SPB_WIN_OPT_* */
+    float* frame_T;                 /* [n_frames][16] camera-to-world, row-major */
+    float* frame_aff;               /* [n_frames][2] brightness (a, b), or NULL */
+    float* k;                       /* [seg_total] log-depth seeds, keyframe after keyframe */
+    float* edge_pose;               /* [n_edges][16] inv(T_trg) T_src, rewritten after every update */
+    float* adam_frame;              /* [n_frames][SPB_WIN_ADAM_FRAME], zero-initialised */
+    float* adam_seg;                /* [seg_total][SPB_ADAM_SEG], zero-initialised */
+    float* win_state;               /* [n_windows][SPB_WIN_NSTATE], zero-initialised */
+    float* edge_tw;                 /* [n_edges][12] scratch: twist gradient of the edge, target side | source side */
+} SpbWindow;
+
+/* edge_pose[e] = inv(T_trg) T_src for every edge (call once before the first iteration). */
+int spb_window_poses(const SpbWindow* win, void* stream);
+
+/* The update alone, from the per-edge gradients spb_grad_accumulate left in out_pair [n_edges][SPB_PAIR_NOUT] and
+ * out_gk (indexed edge_seg_off[e] + b).  Hyper-parameters as torch.optim.Adam holds them (the reference's groups:
+ * lr_k 1e-2, lr_pose 1e-4 / 1e-2 at monocular initialisation, lr_aff 1e-5; :579-586).  stop_tol > 0 reproduces the
+ * early stop (:907-915): once |loss - previous| / previous < stop_tol the window is marked converged after that
+ * step and later calls leave it untouched. */
+int spb_window_update(const SpbWindow* win, const float* out_pair, const float* out_gk, double lr_pose, double lr_k,
+                      double lr_aff, double beta1, double beta2, double eps, double stop_tol, void* stream);
+
+/* One complete mapping iteration for every window: spb_grad_accumulate over all edges (pairs[e] = edge e, seg_off =
+ * edge_seg_off) + spb_window_update; three launches, no host synchronisation. */
+int spb_window_iterate(const SpbGeom* geoms, const SpbPair* pairs, const SpbWindow* win, int max_tiles, int with_affine,
+                       float* work, int64_t work_stride, float* out_pair, float* out_gk, double lr_pose, double lr_k,
+                       double lr_aff, double beta1, double beta2, double eps, double stop_tol, void* ev_before,
+                       void* ev_after, void* stream);
+
 /* CTAs per pair the batched launches use for (max_tiles, n_pairs): the workspace stride must be
  * >= ctas * nacc + max_tiles * nseg floats (nacc/nseg = 16/1 gradient, 47/10 GN). */
 int spb_gn_ctas(int max_tiles, int n_pairs);

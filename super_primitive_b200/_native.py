@@ -22,6 +22,9 @@ GN_NA = 36
 LM_NSTATE = 8
 ADAM_PAIR = 24
 ADAM_SEG = 2
+WIN_OPT_POSE, WIN_OPT_AFF, WIN_OPT_SEEDS = 1, 2, 4
+WIN_ADAM_FRAME = 16
+WIN_NSTATE = 8
 MAX_INLINE_PAIRS = 16
 
 
@@ -49,6 +52,16 @@ class SpbStats(C.Structure):
                 ("residual_raw", C.c_void_p), ("trg_ok", C.c_void_p), ("full_mask", C.c_void_p)]
 
 
+class SpbWindow(C.Structure):
+    _fields_ = [("n_windows", C.c_int32), ("n_frames", C.c_int32), ("n_edges", C.c_int32), ("seg_total", C.c_int32),
+                ("win_frame_off", C.c_void_p), ("win_edge_off", C.c_void_p), ("edge_src", C.c_void_p),
+                ("edge_trg", C.c_void_p), ("edge_w", C.c_void_p), ("edge_seg_off", C.c_void_p),
+                ("frame_seg_off", C.c_void_p), ("frame_seg_cnt", C.c_void_p), ("frame_flags", C.c_void_p),
+                ("frame_T", C.c_void_p), ("frame_aff", C.c_void_p), ("k", C.c_void_p), ("edge_pose", C.c_void_p),
+                ("adam_frame", C.c_void_p), ("adam_seg", C.c_void_p), ("win_state", C.c_void_p),
+                ("edge_tw", C.c_void_p)]
+
+
 _vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 _PROTOS = {
     "spb_compact_count": (_i, [_vp, _i, _i, _i, _vp, _vp]),
@@ -70,6 +83,10 @@ _PROTOS = {
     "spb_adam_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _d, _d, _vp]),
     "spb_adam_iterate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d,
                               _d, _d, _d, _vp, _vp, _vp]),
+    "spb_window_poses": (_i, [C.POINTER(SpbWindow), _vp]),
+    "spb_window_update": (_i, [C.POINTER(SpbWindow), _vp, _vp, _d, _d, _d, _d, _d, _d, _d, _vp]),
+    "spb_window_iterate": (_i, [_vp, _vp, C.POINTER(SpbWindow), _i, _i, _vp, _i64, _vp, _vp, _d, _d, _d, _d, _d, _d, _d,
+                                _vp, _vp, _vp]),
     "spb_lm_saved_floats": (_i, [_i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
     "spb_lm_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spb_dense_depths": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp]),

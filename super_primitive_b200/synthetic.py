@@ -203,3 +203,38 @@ def planar_scene_pair(H, W, N, pose_true, z0=2.0, kind="strips", seed=0):
     trg = KeyFrame(trg_img.float(), K.float())
     k_true = torch.full((N,), math.log(z0), dtype=torch.float32)
     return src, trg, k_true
+
+
+def mapping_window(H, W, N, n_kf=3, n_supp=1, kind="overlap", seed=0, noise=0.01, affine=True, window_full=True,
+                   dtype=torch.float32):
+    """One mapping window in the reference's shape (odometery/odometery.py:451-479, 576-648, 798-820): ``n_kf``
+    keyframes connected to their neighbours (i -> i-1, i+1) plus ``n_supp`` supporting frames per keyframe that serve
+    as targets of their own keyframe AND of the next one; the first keyframe's pose and brightness are held, and its
+    seeds too when the window is full.  Returns {'frames': [...], 'edges': [...]} (see window.py)."""
+    frames, supp_of = [], [[] for _ in range(n_kf)]
+    for i in range(n_kf):
+        kf = make_keyframe(H, W, N, kind=kind, seed=seed + 7 * i, noise=noise, shift=(1.7 * i, 0.9 * i), dtype=dtype)
+        T = small_pose(0.02 * i, -0.004 * i, 0.003 * i, 0.003 * i, -0.002 * i, 0.0015 * i, dtype=dtype)
+        frames.append(dict(T=T, image=kf.image, K=kf.K, kf=kf,
+                           k=torch.full((N,), math.log(2.0) + 0.01 * i, dtype=dtype),
+                           aff=torch.tensor([0.02 * i, -0.01 * i], dtype=dtype) if affine else None,
+                           opt_pose=i > 0, opt_aff=affine and i > 0, opt_seeds=(i > 0) or not window_full))
+    for i in range(n_kf):
+        for j in range(n_supp):
+            a = i + (j + 1) / (n_supp + 1.0)
+            fr = make_keyframe(H, W, N, seed=seed + 100 + 13 * i + j, noise=noise, shift=(1.7 * a, 0.9 * a),
+                               supporting=True, dtype=dtype)
+            T = small_pose(0.02 * a, -0.004 * a, 0.003 * a, 0.003 * a, -0.002 * a, 0.0015 * a, dtype=dtype)
+            supp_of[i].append(len(frames))
+            frames.append(dict(T=T, image=fr.image, K=fr.K, kf=None, k=None,
+                               aff=torch.tensor([0.01 * a, 0.005 * a], dtype=dtype) if affine else None,
+                               opt_pose=True, opt_aff=affine, opt_seeds=False))
+    edges = []
+    for s in range(n_kf):
+        if s > 0:
+            edges.append((s, s - 1))
+        if s < n_kf - 1:
+            edges.append((s, s + 1))
+        for ss in ([s, s - 1] if s > 0 else [s]):
+            edges.extend((s, t) for t in supp_of[ss])
+    return dict(frames=frames, edges=edges)

@@ -280,8 +280,6 @@ def main():
     case_completion("completion", 60, 80, 12, seed=19)
 
 
-if __name__ == "__main__" and "--pyramid-only" not in sys.argv and "--completion-only" not in sys.argv:
-    main()
 
 
 def case_pyramid(name, H, W, N, seed):
@@ -343,7 +341,37 @@ def case_completion(name, H, W, N, seed):
     print(f"{name}: wrote {os.path.getsize(path) / 1e3:.0f} kB")
 
 
-if __name__ == "__main__" and "--pyramid-only" in sys.argv:
-    case_pyramid("pyramid_odd", 45, 70, 4, seed=17)
-if __name__ == "__main__" and "--completion-only" in sys.argv:
-    case_completion("completion", 60, 80, 12, seed=19)
+def case_renorm(name, seed):
+    """renormalise_se3 (lie/lie_algebra.py:41-48), the pose clean-up of the mapping loop (odometery/odometery.py:867,
+    880), run from the reference's own module on slightly denormalised poses -- incl. rotations near pi so that all
+    four quaternion candidates are exercised.  lie/lie_algebra.py imports lietorch (absent, unpinned) at module
+    level without using it in these functions: an empty stub module stands in for the import."""
+    sys.modules.setdefault("lietorch", types.ModuleType("lietorch"))
+    from lie import lie_algebra as ref_la
+    from oracle import window_loop as wl
+    from oracle.adam_loop import exp_se3
+    g = torch.Generator().manual_seed(seed)
+    T_in, T_out = [], []
+    for i in range(48):
+        xi = torch.randn(6, generator=g, dtype=torch.float64) * (0.5 if i % 2 else 3.0)
+        T = exp_se3(xi).float()
+        T[:3] += 1e-3 * torch.randn(3, 4, generator=g)
+        ref = ref_la.renormalise_se3(T.clone())
+        same(ref, wl.renormalise(T), f"{name}/{i}")
+        T_in.append(t2n(T))
+        T_out.append(t2n(ref))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, T_in=np.stack(T_in), T_out=np.stack(T_out))
+    print(f"{name}: wrote {os.path.getsize(path) / 1e3:.0f} kB")
+
+
+if __name__ == "__main__":
+    if "--pyramid-only" in sys.argv:
+        case_pyramid("pyramid_odd", 45, 70, 4, seed=17)
+    elif "--completion-only" in sys.argv:
+        case_completion("completion", 60, 80, 12, seed=19)
+    elif "--renorm-only" in sys.argv:
+        case_renorm("renorm", seed=23)
+    else:
+        main()
+        case_renorm("renorm", seed=23)
