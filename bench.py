@@ -365,6 +365,50 @@ def time_device_loop_single_pair(device, iters=200):
     return out
 
 
+def time_mapping_windows(device, n_windows=8, iters=60):
+    """Windowed mapping (odometery/odometery.py:687-915) through the device-resident window iteration
+    (spb_window_iterate): `n_windows` independent windows of 3 keyframes + 3 supporting frames at the TUM shape
+    (288x224 after downsample_pow 1, 64 segments), 9 edges each; one iteration = batched gradient kernel over all
+    edges + finalize + coupled Adam update / pose bookkeeping (three launches, no host sync)."""
+    from super_primitive_b200 import synthetic as syn
+    from super_primitive_b200.window import MappingWindows
+    wins = []
+    for i in range(n_windows):
+        w = syn.mapping_window(224, 288, 64, n_kf=3, n_supp=1, kind="overlap", seed=50 + i, affine=True)
+        for f in w['frames']:
+            for key in ('T', 'image', 'K', 'aff', 'k'):
+                f[key] = None if f[key] is None else f[key].to(device)
+            if f['kf'] is not None:
+                f['kf'] = f['kf'].to(device)
+                f['image'] = f['kf'].image
+        wins.append(w)
+    mw = MappingWindows(wins)
+    mw.run(10)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    mw.run(iters)
+    b.record()
+    torch.cuda.synchronize()
+    eager_ms = a.elapsed_time(b) / iters
+    graph = mw.capture(20)
+    graph.replay()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(3):
+        graph.replay()
+    b.record()
+    torch.cuda.synchronize()
+    graph_ms = a.elapsed_time(b) / 60
+    best = min(eager_ms, graph_ms)
+    return {"windows": n_windows, "edges": mw.n_edges, "frames": mw.n_frames,
+            "eager_us_per_iter": 1e3 * eager_ms, "graph_us_per_iter": 1e3 * graph_ms,
+            "window_iters_per_s": n_windows * 1e3 / best, "edge_iters_per_s": mw.n_edges * 1e3 / best,
+            "algorithmic_GBps": mw.algorithmic_bytes_per_iter() / (best * 1e-3) / 1e9,
+            "what": "device-resident mapping windows (3 keyframes + 3 supporting frames, 9 edges, 288x224, 64 segments, "
+                    "brightness terms on): gradient kernel over all edges + finalize + coupled Adam/pose update"}
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -486,10 +530,11 @@ def main():
 
     # ---- drop-in arm: the reference's own loop (photomeric_cost -> backward -> Adam.step) through the public
     #      Python surface, ONE pair, device-resident inputs: launch/host-bound, reported for context -------------
-    dropin = device_loop = None
+    dropin = device_loop = mapping = None
     if rank == 0 and not args.no_e2e:
         dropin = time_dropin_single_pair(device)
         device_loop = time_device_loop_single_pair(device)
+        mapping = time_mapping_windows(device)
 
     # ---- the only collective of the path: final gather of poses / seeds / cost -------------------------
     gather_ms = None
@@ -550,6 +595,7 @@ def main():
         if dropin is not None:
             line["dropin_single_pair"] = dropin
             line["device_loop_single_pair"] = device_loop
+            line["mapping_windows"] = mapping
         if gather_ms is not None:
             line["final_gather_ms"] = gather_ms
         print(json.dumps(line), flush=True)

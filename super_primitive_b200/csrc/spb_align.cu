@@ -491,12 +491,32 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
         pseg.zero();
         // padding entries of a partial tile are zero words: uv bit 31 clear => invalid, no bounds test needed
         (void)cnt;
+#if SPB_TAP_PREFETCH
+        // software pipeline with L1 as the buffer: the next point of the lane is projected and its four taps are
+        // requested into L1 (CCTL.PF1, no destination register) before the current point is consumed, so the
+        // demand loads of the next iteration find the lines on their way instead of starting a DRAM/L2 round trip;
+        // only the projected state (not 16 tap registers) stays live across the arithmetic of the current point
+        Proj qn;
+        bool okn = project_point(c, s_uv[lane], s_f[SPB_TILE + lane], shift, Wl, qn);
+        if constexpr (PACKED) okn = okn && qn.live;
+        if (okn) prefetch_taps(trg, Wl, qn.off);
+#endif
         SPB_PRAGMA_UNROLL(SPB_UNROLL)
         for (int j = 0; j < SPB_PPT; ++j) {
             const int i = j * 32 + lane;
+#if SPB_TAP_PREFETCH
+            const Proj q = qn;
+            const bool ok = okn;
+            if (j + 1 < SPB_PPT) {
+                okn = project_point(c, s_uv[i + 32], s_f[SPB_TILE + i + 32], shift, Wl, qn);
+                if constexpr (PACKED) okn = okn && qn.live;
+                if (okn) prefetch_taps(trg, Wl, qn.off);
+            }
+#else
             Proj q;
             bool ok = project_point(c, s_uv[i], s_f[SPB_TILE + i], shift, Wl, q);
             if constexpr (PACKED) ok = ok && q.live;       // see point_gn6_packed
+#endif
             if (ok) {
                 Taps4 tp;
                 load_taps(trg, Wl, q.off, tp);

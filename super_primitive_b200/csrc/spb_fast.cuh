@@ -185,6 +185,16 @@ __device__ __forceinline__ void load_taps(const float4* __restrict__ trg, int Wl
 #endif
 }
 
+// request the four taps of a point into L1 without a destination register (SASS CCTL.E.PF1)
+#ifndef SPB_TAP_PREFETCH
+#define SPB_TAP_PREFETCH 0                      // 1: project + prefetch one point ahead of the point being consumed
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_taps(const float4* __restrict__ trg, int Wl, int off) {
+    const float4* p0 = trg + off;
+    prefetch_l1(p0); prefetch_l1(p0 + 1); prefetch_l1(p0 + Wl); prefetch_l1(p0 + Wl + 1);
+}
+
 // ---- Gauss-Newton mode, scalar formulation (used by the 8-column / affine variant) ---------------------
 // (the 6-column GN path and the gradient mode live in spb_gn_packed.cuh, written with packed FP32)
 // acc layout = upper triangle of the NPxNP pose block (row-major packed), g_p[NP], cost, wcost, nvalid
