@@ -534,7 +534,10 @@ def main():
     if rank == 0 and not args.no_e2e:
         dropin = time_dropin_single_pair(device)
         device_loop = time_device_loop_single_pair(device)
-        mapping = time_mapping_windows(device)
+        try:            # auxiliary figure (a 'next' row of SURVEY 8(f)): its failure must not take the headline line down
+            mapping = time_mapping_windows(device)
+        except Exception as e:      # noqa: BLE001
+            mapping = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- the only collective of the path: final gather of poses / seeds / cost -------------------------
     gather_ms = None
