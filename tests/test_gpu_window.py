@@ -133,7 +133,7 @@ def test_single_edge_window_equals_the_tracker_iteration():
     torch.cuda.synchronize()
     np.testing.assert_allclose(to_np(mw.edge_pose[0]).reshape(4, 4), to_np(batch.poses_matrix()[0]), atol=5e-6)
     np.testing.assert_allclose(to_np(mw.seeds_of(0)), to_np(batch.k_of(0)), atol=5e-6)
-    np.testing.assert_allclose(float(mw.losses()[0]), float(batch.grad_costs()[0]), rtol=1e-5)
+    np.testing.assert_allclose(float(mw.losses()[0]), float(batch.grad_costs()[0]), rtol=1e-4)
 
 
 def test_graph_replay_and_early_stop():
