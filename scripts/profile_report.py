@@ -50,7 +50,7 @@ for mode in ("gn", "grad"):
             wr = float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[unit]
     if rd is not None and wr is not None:
         traffic[f"{mode}_bytes_per_launch_64pairs"] = rd + wr
-if traffic:
+if traffic and "_" not in tag:      # variant visits (<variant>_<tag>) never replace the default library's traffic figure
     traffic["source"] = f"ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, visit {tag}"
     json.dump(traffic, open(f"{out}/traffic.json", "w"), indent=1)
 lines = []
@@ -64,4 +64,4 @@ if lines:
 for extra in (f"pytest_{tag}.log", f"smoke_{tag}.log", f"gpu_{tag}.txt"):
     if os.path.exists(f"{src}/{extra}"):
         shutil.copy(f"{src}/{extra}", f"{out}/{tag}_{extra.replace('_' + tag, '')}")
-print("wrote", sorted(os.listdir(out)))
+print("wrote", sorted(n for n in os.listdir(out) if n.startswith(tag)))

@@ -462,12 +462,6 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
 
     const float4* trg = reinterpret_cast<const float4*>(pr.trg_rgba);
     const int Wl = pr.Wl;
-#if SPB_TAP_PREFETCH == 2
-    // per-warp tap buffer [4 taps][32 lanes] float4 behind the ring and its barriers
-    const float4* tapbuf = reinterpret_cast<const float4*>(s_dyn + SPB_WARPS * SPB_WSTAGES * SPB_SLOT_WORDS +
-                                                           SPB_WARPS * SPB_WSTAGES * 2) + warp * 128;
-    const uint32_t tap_u32 = smem_u32(tapbuf + lane);
-#endif
     constexpr bool PACKED = (MODE == MODE_GN && NP == 6);   // FFMA2 formulation (spb_gn_packed.cuh)
     float acc[NACC];
 #pragma unroll
@@ -497,58 +491,15 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
         pseg.zero();
         // padding entries of a partial tile are zero words: uv bit 31 clear => invalid, no bounds test needed
         (void)cnt;
-#if SPB_TAP_PREFETCH == 2
-        // software pipeline with SHARED MEMORY as the buffer: the four taps of the lane's next point travel
-        // global -> shared with cp.async (LDGSTS, no destination registers) while the current point is consumed;
-        // each lane owns 4 x 16 bytes of the warp's tap buffer, so completion is the lane's own wait_group
-        Proj qn;
-        bool okn = project_point(c, s_uv[lane], s_f[SPB_TILE + lane], shift, Wl, qn);
-        if constexpr (PACKED) okn = okn && qn.live;
-        if (okn) stage_taps(tap_u32, trg, Wl, qn.off);
-        cp_async_commit();
-#elif SPB_TAP_PREFETCH
-        // software pipeline with L1 as the buffer: the next point of the lane is projected and its four taps are
-        // requested into L1 (CCTL.PF1, no destination register) before the current point is consumed, so the
-        // demand loads of the next iteration find the lines on their way instead of starting a DRAM/L2 round trip;
-        // only the projected state (not 16 tap registers) stays live across the arithmetic of the current point
-        Proj qn;
-        bool okn = project_point(c, s_uv[lane], s_f[SPB_TILE + lane], shift, Wl, qn);
-        if constexpr (PACKED) okn = okn && qn.live;
-        if (okn) prefetch_taps(trg, Wl, qn.off);
-#endif
         SPB_PRAGMA_UNROLL(SPB_UNROLL)
         for (int j = 0; j < SPB_PPT; ++j) {
             const int i = j * 32 + lane;
-#if SPB_TAP_PREFETCH == 2
-            const Proj q = qn;
-            const bool ok = okn;
-            Taps4 tp;
-            cp_async_wait_all();
-            if (ok) { tp.nw = tapbuf[lane]; tp.ne = tapbuf[32 + lane]; tp.sw = tapbuf[64 + lane]; tp.se = tapbuf[96 + lane]; }
-            if (j + 1 < SPB_PPT) {
-                okn = project_point(c, s_uv[i + 32], s_f[SPB_TILE + i + 32], shift, Wl, qn);
-                if constexpr (PACKED) okn = okn && qn.live;
-                if (okn) stage_taps(tap_u32, trg, Wl, qn.off);
-                cp_async_commit();
-            }
-#elif SPB_TAP_PREFETCH
-            const Proj q = qn;
-            const bool ok = okn;
-            if (j + 1 < SPB_PPT) {
-                okn = project_point(c, s_uv[i + 32], s_f[SPB_TILE + i + 32], shift, Wl, qn);
-                if constexpr (PACKED) okn = okn && qn.live;
-                if (okn) prefetch_taps(trg, Wl, qn.off);
-            }
-#else
             Proj q;
             bool ok = project_point(c, s_uv[i], s_f[SPB_TILE + i], shift, Wl, q);
             if constexpr (PACKED) ok = ok && q.live;       // see point_gn6_packed
-#endif
             if (ok) {
-#if SPB_TAP_PREFETCH != 2
                 Taps4 tp;
                 load_taps(trg, Wl, q.off, tp);
-#endif
                 const float i0 = s_f[2 * SPB_TILE + i], i1 = s_f[3 * SPB_TILE + i], i2 = s_f[4 * SPB_TILE + i];
                 if constexpr (MODE == MODE_GRAD)
                     point_grad_packed<AFF>(c, tp, q, i0, i1, i2, gacc, seg[0]);

@@ -23,11 +23,7 @@
 #endif
 #define SPB_SLOT_WORDS SPB_PACK_WORDS           // one tile block: header {seg, cnt, unpadded start, -} + 5 arrays
 #define SPB_NSHIFT 512                         // segments whose shift is cached in shared memory
-#ifndef SPB_TAP_PREFETCH
-#define SPB_TAP_PREFETCH 0                      // 1: project + L1 prefetch one point ahead; 2: cp.async taps into shared memory one point ahead
-#endif
-#define SPB_TAPBUF_BYTES ((SPB_TAP_PREFETCH == 2) ? SPB_WARPS * 4 * 32 * 16 : 0)
-#define SPB_FAST_DYN_SMEM (SPB_WARPS * SPB_WSTAGES * SPB_SLOT_WORDS * 4 + SPB_WARPS * SPB_WSTAGES * 8 + SPB_TAPBUF_BYTES)
+#define SPB_FAST_DYN_SMEM (SPB_WARPS * SPB_WSTAGES * SPB_SLOT_WORDS * 4 + SPB_WARPS * SPB_WSTAGES * 8)
 
 // context words, grouped so the hot loop reads them as eight 16-byte vectors (LDS.128):
 //   V0..V2 = rows of [M | t] with M = R diag(1/fx, 1/fy, 1);  V3 = (ax, bx, ay, by);  V4 = (sx, sy, tau, ea);
@@ -193,25 +189,6 @@ __device__ __forceinline__ void load_taps(const float4* __restrict__ trg, int Wl
 #else
     t.nw = __ldg(p0); t.ne = __ldg(p0 + 1); t.sw = __ldg(p0 + Wl); t.se = __ldg(p0 + Wl + 1);
 #endif
-}
-
-// request the four taps of a point into L1 without a destination register (SASS CCTL.E.PF1)
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_taps(const float4* __restrict__ trg, int Wl, int off) {
-    const float4* p0 = trg + off;
-    prefetch_l1(p0); prefetch_l1(p0 + 1); prefetch_l1(p0 + Wl); prefetch_l1(p0 + Wl + 1);
-}
-
-// asynchronous 16-byte copies global -> shared (LDGSTS): no destination register, completion per thread
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-// dst = shared address of the lane's slot of tap 0; taps are 32 lanes x 16 bytes apart
-__device__ __forceinline__ void stage_taps(uint32_t dst, const float4* __restrict__ trg, int Wl, int off) {
-    const float4* p0 = trg + off;
-    cp_async16(dst, p0); cp_async16(dst + 512, p0 + 1); cp_async16(dst + 1024, p0 + Wl); cp_async16(dst + 1536, p0 + Wl + 1);
 }
 
 // ---- Gauss-Newton mode, scalar formulation (used by the 8-column / affine variant) ---------------------
