@@ -119,6 +119,33 @@ int spb_sample_source(const SpbGeom* geom, const float* src_planar, int Hl, int 
  * g[128] + b[128] (zero-filled beyond count).  src_rgb = output of spb_sample_source for the level. */
 int spb_build_tile_pack(const SpbGeom* geom, const float* src_rgb, uint32_t* pack, void* stream);
 
+/* ============================ frame ingest (once per frame, many pairs per launch) ============ */
+
+/* image_tt (tool/etc.py:37-40): HWC uint8 frame -> float32 CHW in [0,1], the same float32 division by 255 the
+ * reference performs on the host before uploading 12 bytes per pixel; here 3 bytes per pixel travel. */
+int spb_image_tt(const uint8_t* hwc, int H, int W, float* chw, void* stream);
+
+/* One (source keyframe, target frame) pair whose frames arrive as 8-bit HWC images (device copies of what the dataset
+ * readers deliver: data/replica.py:55, data/tum_undistort.py:112).  Any of the two halves may be skipped with NULLs. */
+typedef struct SpbFrameJob {
+    const uint8_t* src_u8;     /* [Hl][Wl][3] source level image, or NULL                                   */
+    const uint8_t* trg_u8;     /* [Hl][Wl][3] target level image, or NULL                                   */
+    float*    src_planar;      /* out [3][Hl][Wl]  image_tt(src)                                             */
+    float*    src_rgb;         /* out [3][n_pad]   spb_sample_source(src_planar)                             */
+    uint32_t* pack;            /* out [n_tiles][SPB_PACK_WORDS]  spb_build_tile_pack(src_rgb)                */
+    float*    trg_rgba;        /* out [Hl][Wl][4]  spb_pack_rgba(image_tt(trg))                              */
+    int32_t geom;              /* index into the geometry array                                             */
+    int32_t Hl, Wl;
+    int32_t pad_;
+} SpbFrameJob;
+
+/* Ingest n_jobs pairs in THREE launches (grid.y = job): image_tt + re-layout of both frames, cached source samples,
+ * tile-major level buffer -- bit-identical to spb_image_tt / spb_pack_rgba / spb_sample_source / spb_build_tile_pack
+ * applied pair by pair.  geoms / jobs: DEVICE arrays; max_pixels / max_pad / max_tiles: maxima over the jobs (grid
+ * sizing only). */
+int spb_ingest_u8(const SpbGeom* geoms, const SpbFrameJob* jobs, int n_jobs, int max_pixels, int max_pad,
+                  int max_tiles, void* stream);
+
 /* ================================ per-iteration hot path ====================================== */
 
 /* Fused residual + first-order gradient for B pairs sharing geometry `geom` (host struct, device

@@ -52,6 +52,12 @@ class SpbStats(C.Structure):
                 ("residual_raw", C.c_void_p), ("trg_ok", C.c_void_p), ("full_mask", C.c_void_p)]
 
 
+class SpbFrameJob(C.Structure):
+    _fields_ = [("src_u8", C.c_void_p), ("trg_u8", C.c_void_p), ("src_planar", C.c_void_p), ("src_rgb", C.c_void_p),
+                ("pack", C.c_void_p), ("trg_rgba", C.c_void_p), ("geom", C.c_int32), ("Hl", C.c_int32),
+                ("Wl", C.c_int32), ("pad_", C.c_int32)]
+
+
 class SpbWindow(C.Structure):
     _fields_ = [("n_windows", C.c_int32), ("n_frames", C.c_int32), ("n_edges", C.c_int32), ("seg_total", C.c_int32),
                 ("win_frame_off", C.c_void_p), ("win_edge_off", C.c_void_p), ("edge_src", C.c_void_p),
@@ -70,6 +76,8 @@ _PROTOS = {
     "spb_pack_rgba": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
     "spb_sample_source": (_i, [C.POINTER(SpbGeom), _vp, _i, _i, _vp, _vp]),
     "spb_build_tile_pack": (_i, [C.POINTER(SpbGeom), _vp, _vp, _vp]),
+    "spb_image_tt": (_i, [_vp, _i, _i, _vp, _vp]),
+    "spb_ingest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "spb_cost_grad": (_i, [C.POINTER(SpbGeom), C.POINTER(SpbPair), _i, _vp, _vp, _vp, _vp, _vp,
                            C.POINTER(SpbStats), _vp]),
     "spb_cost_grad_points": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SpbPair), _vp, _vp, _vp]),

@@ -1,0 +1,72 @@
+"""Frame ingest: 8-bit frames in, everything the fused alignment kernel streams out.
+
+The reference turns a dataset frame (HWC uint8 from cv2: data/replica.py:55, data/tum_undistort.py:112) into a float
+tensor on the HOST (`tool.etc.image_tt`, tool/etc.py:37-40: ``(torch.from_numpy(image) / 255.).float().to(device)`` then
+HWC -> CHW) and uploads 12 bytes per pixel.  Here the 3-byte pixels are uploaded and `image_tt` runs on the device with
+the same float32 division, so the resulting frames are bit-identical (checked on the GPU against torch).
+
+``image_tt``      mirror of the reference helper for one frame (uint8 HWC tensor, host or device).
+``FrameIngest``   many (source keyframe, target frame) pairs per launch: `spb_ingest_u8` re-derives the RGBA target, the
+                  cached source samples and the tile-major level buffer of every pair in three launches
+                  (include/spb200.h) -- what `bench.py`'s end-to-end arm runs every step.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as nat
+from .geometry import _stream
+from .solver import _struct_array_to_device
+
+
+def image_tt(image, device="cuda"):
+    """tool/etc.py:37-40: HWC uint8 frame (numpy array or tensor) -> (3,H,W) float32 in [0,1] on ``device``."""
+    t = torch.as_tensor(image)
+    if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
+        raise AssertionError("image_tt expects an HWC uint8 frame with 3 channels")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("super_primitive_b200 runs on CUDA tensors only (no CPU fallback)")
+    t = t.to(dev, non_blocking=True).contiguous()
+    H, W = int(t.shape[0]), int(t.shape[1])
+    out = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    nat.check(nat.lib().spb_image_tt(t.data_ptr(), H, W, out.data_ptr(), _stream()), "spb_image_tt")
+    return out
+
+
+class FrameIngest:
+    """Device-side ingest of the frames of ``problems`` (dicts as `solver.AlignmentBatch` takes them: geom, src_rgb, pack,
+    trg_rgba; the level size is the target's).  ``src_u8`` / ``trg_u8``: per problem a device uint8 (Hl,Wl,3) staging
+    tensor that the caller fills (H2D copy) before `run`."""
+
+    def __init__(self, problems, geoms):
+        dev = problems[0]['trg_rgba'].device
+        gidx = {id(g): i for i, g in enumerate(geoms)}
+        self.n = len(problems)
+        self.src_u8, self.trg_u8, self.src_planar = [], [], []
+        jarr = (nat.SpbFrameJob * self.n)()
+        self.max_pixels = self.max_pad = self.max_tiles = 1
+        for i, p in enumerate(problems):
+            Hl, Wl = int(p['trg_rgba'].shape[0]), int(p['trg_rgba'].shape[1])
+            g = p['geom']
+            su = torch.empty((Hl, Wl, 3), dtype=torch.uint8, device=dev)
+            tu = torch.empty((Hl, Wl, 3), dtype=torch.uint8, device=dev)
+            pl = torch.empty((3, Hl, Wl), dtype=torch.float32, device=dev)
+            self.src_u8.append(su)
+            self.trg_u8.append(tu)
+            self.src_planar.append(pl)
+            j = jarr[i]
+            j.src_u8, j.trg_u8, j.src_planar = su.data_ptr(), tu.data_ptr(), pl.data_ptr()
+            j.src_rgb, j.pack, j.trg_rgba = p['src_rgb'].data_ptr(), p['pack'].data_ptr(), p['trg_rgba'].data_ptr()
+            j.geom, j.Hl, j.Wl = gidx[id(g)], Hl, Wl
+            self.max_pixels = max(self.max_pixels, Hl * Wl)
+            self.max_pad = max(self.max_pad, g.P_pad)
+            self.max_tiles = max(self.max_tiles, g.n_tiles)
+        self.d_jobs = _struct_array_to_device(jarr, dev)
+        self.job_bytes = __import__("ctypes").sizeof(nat.SpbFrameJob)
+
+    def run(self, d_geoms, first=0, count=None):
+        """Ingest jobs [first, first + count) on the current stream (three launches)."""
+        count = self.n - first if count is None else count
+        nat.check(nat.lib().spb_ingest_u8(d_geoms.data_ptr(), self.d_jobs.data_ptr() + first * self.job_bytes, count,
+                                          self.max_pixels, self.max_pad, self.max_tiles, _stream()), "spb_ingest_u8")

@@ -39,6 +39,8 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_native.SpbGeom) == 6 * 8 + 6 * 4
     assert ctypes.sizeof(_native.SpbPair) == 8 * 8 + 4 * 4
     assert ctypes.sizeof(_native.SpbStats) == 6 * 8
+    assert ctypes.sizeof(_native.SpbFrameJob) == 6 * 8 + 4 * 4
+    assert ctypes.sizeof(_native.SpbWindow) == 4 * 4 + 17 * 8
 
 
 def test_argument_validation_without_gpu():
@@ -50,6 +52,11 @@ def test_argument_validation_without_gpu():
     assert lib.spb_cost_grad(None, None, 1, None, None, None, None, None, None, None) == -1
     assert lib.spb_gn_accumulate(None, None, None, 1, 1, 1e-3, 0, None, 0, None, None, None, None, None) == -1
     assert lib.spb_segment_reinit(None, None, 1, None, None, None, None, None) == -1
+    assert lib.spb_image_tt(None, 4, 4, None, None) == -1
+    assert lib.spb_ingest_u8(None, None, 1, 1, 1, 1, None) == -1
+    assert lib.spb_window_poses(None, None) == -1
+    empty = _native.SpbWindow()
+    assert lib.spb_window_update(ctypes.byref(empty), None, None, 1e-4, 1e-2, 1e-5, 0.9, 0.999, 1e-8, 0.0, None) == -1
 
 
 def test_install_as_core_aliases_modules():
