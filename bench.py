@@ -165,9 +165,12 @@ class HostStaged:
             self.packed_host.append((p['pack'].cpu().pin_memory(), p['trg_rgba'].cpu().pin_memory()))
         from super_primitive_b200.frames import FrameIngest
         self.ingest = FrameIngest(problems, batch.geoms)
-        self.u8_host = [(p['src_u8'].cpu().pin_memory(), p['trg_u8'].cpu().pin_memory()) for p in problems]
+        self.arena = self.ingest.host_arena()          # pinned arena a loader decodes the 8-bit frames into
+        for i, p in enumerate(problems):
+            self.ingest.fill(self.arena, i, p['src_u8'].cpu(), p['trg_u8'].cpu())
         self.chunk = max(1, int(chunk))                # pairs per ingest launch group (copy/compute overlap)
         self.chunk_events = [torch.cuda.Event() for _ in range((len(problems) + self.chunk - 1) // self.chunk)]
+        self.consumed = []
         self.h_pose = batch.poses.cpu().pin_memory()
         self.h_k = batch.k.cpu().pin_memory()
         self.o_pose = torch.empty_like(self.h_pose).pin_memory()
@@ -175,7 +178,7 @@ class HostStaged:
         self.o_cost = torch.empty((batch.n, 8), dtype=torch.float32).pin_memory()
         nbytes = lambda pairs: sum(t.numel() * t.element_size() for pr in pairs for t in pr)   # noqa: E731
         self.params_bytes = self.h_pose.numel() * 4 + self.h_k.numel() * 4
-        self.h2d = {"u8": nbytes(self.u8_host) + self.params_bytes, "raw": nbytes(self.raw_host) + self.params_bytes,
+        self.h2d = {"u8": self.ingest.offsets[-1] + self.params_bytes,      # bytes actually copied (16-byte aligned frames) "raw": nbytes(self.raw_host) + self.params_bytes,
                     "packed": nbytes(self.packed_host) + self.params_bytes, "params": self.params_bytes}
         self.d2h = (self.o_pose.numel() + self.o_k.numel() + self.o_cost.numel()) * 4
         self.copy_stream = torch.cuda.Stream()
@@ -188,17 +191,24 @@ class HostStaged:
         main = torch.cuda.current_stream()
         if mode == "u8":
             cs, ing, n = self.copy_stream, self.ingest, len(self.problems)
-            cs.wait_stream(main)                      # the previous step's consumers of the staging buffers are done
+            if len(self.consumed) != len(self.chunk_events):
+                self.consumed = [None] * len(self.chunk_events)
             with torch.cuda.stream(cs):
                 for c, ev in enumerate(self.chunk_events):
-                    for i in range(c * self.chunk, min(n, (c + 1) * self.chunk)):
-                        ing.src_u8[i].copy_(self.u8_host[i][0], non_blocking=True)
-                        ing.trg_u8[i].copy_(self.u8_host[i][1], non_blocking=True)
+                    first = c * self.chunk
+                    if self.consumed[c] is not None:
+                        cs.wait_event(self.consumed[c])     # the previous step's ingest has read this part of the staging buffer
+                    ing.upload(self.arena, first, min(n, first + self.chunk) - first)      # one copy per chunk
                     ev.record(cs)
             for c, ev in enumerate(self.chunk_events):
                 main.wait_event(ev)
                 first = c * self.chunk
                 ing.run(b.d_geoms, first, min(n, first + self.chunk) - first)
+                if self.consumed[c] is None:
+                    self.consumed[c] = torch.cuda.Event()
+                self.consumed[c].record(main)
+            # (the copies of the NEXT step may start as soon as its chunk has been ingested: they overlap this step's
+            #  iteration; the derived buffers are written and read on the compute stream only, so they need no second copy)
         elif mode == "raw":
             lib, nat = self.nat.lib(), self.nat
             cs = self.copy_stream

@@ -36,34 +36,66 @@ def image_tt(image, device="cuda"):
 
 class FrameIngest:
     """Device-side ingest of the frames of ``problems`` (dicts as `solver.AlignmentBatch` takes them: geom, src_rgb, pack,
-    trg_rgba; the level size is the target's).  ``src_u8`` / ``trg_u8``: per problem a device uint8 (Hl,Wl,3) staging
-    tensor that the caller fills (H2D copy) before `run`."""
+    trg_rgba; the level size is the target's).
+
+    The 8-bit frames of all problems live in ONE flat device staging buffer ``stage`` (problem after problem: source
+    frame, then target frame, each (Hl,Wl,3) uint8), mirrored by a pinned host arena of the same layout
+    (`host_arena`) that a loader decodes into -- so a chunk of pairs is ONE host->device copy (`upload`) followed by
+    the three launches of `spb_ingest_u8` (`run`)."""
 
     def __init__(self, problems, geoms):
+        import ctypes as C
         dev = problems[0]['trg_rgba'].device
         gidx = {id(g): i for i, g in enumerate(geoms)}
         self.n = len(problems)
-        self.src_u8, self.trg_u8, self.src_planar = [], [], []
+        sizes = [3 * int(p['trg_rgba'].shape[0]) * int(p['trg_rgba'].shape[1]) for p in problems]
+        self.offsets = [0]
+        for b in sizes:
+            self.offsets.append(self.offsets[-1] + 2 * ((b + 15) // 16 * 16))      # 16-byte aligned frames
+        self.stage = torch.empty(self.offsets[-1], dtype=torch.uint8, device=dev)
+        self.src_planar = []
         jarr = (nat.SpbFrameJob * self.n)()
         self.max_pixels = self.max_pad = self.max_tiles = 1
+        self._views = []
         for i, p in enumerate(problems):
             Hl, Wl = int(p['trg_rgba'].shape[0]), int(p['trg_rgba'].shape[1])
             g = p['geom']
-            su = torch.empty((Hl, Wl, 3), dtype=torch.uint8, device=dev)
-            tu = torch.empty((Hl, Wl, 3), dtype=torch.uint8, device=dev)
+            half = (self.offsets[i + 1] - self.offsets[i]) // 2
+            so, to = self.offsets[i], self.offsets[i] + half
+            self._views.append((so, to, Hl, Wl))
             pl = torch.empty((3, Hl, Wl), dtype=torch.float32, device=dev)
-            self.src_u8.append(su)
-            self.trg_u8.append(tu)
             self.src_planar.append(pl)
             j = jarr[i]
-            j.src_u8, j.trg_u8, j.src_planar = su.data_ptr(), tu.data_ptr(), pl.data_ptr()
+            j.src_u8, j.trg_u8, j.src_planar = self.stage.data_ptr() + so, self.stage.data_ptr() + to, pl.data_ptr()
             j.src_rgb, j.pack, j.trg_rgba = p['src_rgb'].data_ptr(), p['pack'].data_ptr(), p['trg_rgba'].data_ptr()
             j.geom, j.Hl, j.Wl = gidx[id(g)], Hl, Wl
             self.max_pixels = max(self.max_pixels, Hl * Wl)
             self.max_pad = max(self.max_pad, g.P_pad)
             self.max_tiles = max(self.max_tiles, g.n_tiles)
         self.d_jobs = _struct_array_to_device(jarr, dev)
-        self.job_bytes = __import__("ctypes").sizeof(nat.SpbFrameJob)
+        self.job_bytes = C.sizeof(nat.SpbFrameJob)
+
+    def host_arena(self):
+        """Pinned host buffer with the layout of ``stage``."""
+        return torch.empty(self.offsets[-1], dtype=torch.uint8).pin_memory()
+
+    def fill(self, arena, i, src_u8, trg_u8):
+        """Write the (Hl,Wl,3) uint8 frames of problem ``i`` into ``arena`` (what a loader does when it decodes)."""
+        so, to, Hl, Wl = self._views[i]
+        n = 3 * Hl * Wl
+        arena[so:so + n].copy_(src_u8.reshape(-1))
+        arena[to:to + n].copy_(trg_u8.reshape(-1))
+
+    def frame_bytes(self, first=0, count=None):
+        """payload bytes (without alignment padding) of the frames of problems [first, first + count)"""
+        count = self.n - first if count is None else count
+        return sum(2 * 3 * v[2] * v[3] for v in self._views[first:first + count])
+
+    def upload(self, arena, first=0, count=None):
+        """ONE asynchronous host->device copy of the frames of problems [first, first + count) on the current stream."""
+        count = self.n - first if count is None else count
+        a, b = self.offsets[first], self.offsets[first + count]
+        self.stage[a:b].copy_(arena[a:b], non_blocking=True)
 
     def run(self, d_geoms, first=0, count=None):
         """Ingest jobs [first, first + count) on the current stream (three launches)."""
