@@ -178,7 +178,8 @@ class HostStaged:
         self.o_cost = torch.empty((batch.n, 8), dtype=torch.float32).pin_memory()
         nbytes = lambda pairs: sum(t.numel() * t.element_size() for pr in pairs for t in pr)   # noqa: E731
         self.params_bytes = self.h_pose.numel() * 4 + self.h_k.numel() * 4
-        self.h2d = {"u8": self.ingest.offsets[-1] + self.params_bytes,      # bytes actually copied (16-byte aligned frames) "raw": nbytes(self.raw_host) + self.params_bytes,
+        self.h2d = {"u8": self.ingest.offsets[-1] + self.params_bytes,      # bytes actually copied (16-byte aligned frames)
+                    "raw": nbytes(self.raw_host) + self.params_bytes,
                     "packed": nbytes(self.packed_host) + self.params_bytes, "params": self.params_bytes}
         self.d2h = (self.o_pose.numel() + self.o_k.numel() + self.o_cost.numel()) * 4
         self.copy_stream = torch.cuda.Stream()
