@@ -44,7 +44,7 @@ def parse():
                     help="gn = IRLS GN/LM iteration; grad = first-order iteration (cost + gradient + Adam update)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunk", type=int, default=16, help="pairs per ingest launch group of the end-to-end arm")
+    ap.add_argument("--e2e-chunk", type=int, default=8, help="pairs per ingest launch group of the end-to-end arm")
     return ap.parse_args()
 
 
@@ -152,7 +152,7 @@ class HostStaged:
     mode "packed": the already derived buffers (tile-major level buffer + RGBA target) are uploaded instead.
     mode "params": frames stay resident, only pose + seeds travel."""
 
-    def __init__(self, batch, problems, chunk=16):
+    def __init__(self, batch, problems, chunk=8):
         from super_primitive_b200 import _native as nat
         self.nat = nat
         self.batch = batch
@@ -554,12 +554,23 @@ def main():
             return pairs_total * e_steps / (float(tt.item()) * 1e-3)
 
         v_u8 = timed("u8")
+        # what the link itself delivers: the same pinned arena copied to the staging buffer with nothing else going on
+        hs.copy_stream.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(5):
+            hs.ingest.upload(hs.arena)
+        p1.record()
+        torch.cuda.synchronize()
+        h2d_gbps = 5 * hs.ingest.offsets[-1] / (p0.elapsed_time(p1) * 1e-3) / 1e9
         v_raw = timed("raw")            # informational: frames converted to float32 on the host (the reference's image_tt)
         v_packed = timed("packed")      # informational: derived buffers uploaded instead of frames
         v_params = timed("params")      # informational: frames resident (as the reference keeps its KeyFrames)
         e2e = {"value": v_u8, "unit": UNIT,
                "h2d_bytes_per_step": int(hs.h2d["u8"]), "d2h_bytes_per_step": int(hs.d2h), "steps": e_steps,
                "gpu_launches_per_step": hs.launches_per_step["u8"],
+               "h2d_link_GBps": h2d_gbps,
+               "frac_of_link": (hs.h2d["u8"] * v_u8 / pairs_total) / 1e9 / h2d_gbps,
                "what": "per step: H2D (pinned) of the 8-bit source + target frames of every pair (HWC uint8, as the "
                        "reference's dataset readers deliver them) + pose + seeds; on the device spb_ingest_u8 (image_tt, "
                        "RGBA target, cached source samples, tile-major level buffer; three launches per chunk of %d pairs, "
