@@ -56,3 +56,30 @@ def gather_results(poses, k_padded, costs, n_units, group=None):
         out_k[ii] = blk[:, 16:16 + nmax]
         out_cost[ii] = blk[:, 16 + nmax]
     return out_pose, out_k, out_cost
+
+
+def gather_ragged(vectors, n_units, group=None):
+    """Variable-length results (one 1-D float32 tensor per LOCAL unit, ordered like ``shard_indices``) -> list of
+    ``n_units`` tensors in unit order on every rank.  Used for mapping windows, whose result (frame poses, seeds of
+    every keyframe, brightness terms, loss) has a window-dependent length: two all-reduces agree on the padded
+    shape, one all-gather moves the NaN-padded rows with their lengths."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return list(vectors)
+    world = dist.get_world_size(group)
+    dev = vectors[0].device if vectors else torch.device("cpu")
+    n_local_max = (n_units + world - 1) // world
+    width = torch.tensor([max((int(v.numel()) for v in vectors), default=0)], dtype=torch.int64, device=dev)
+    dist.all_reduce(width, op=dist.ReduceOp.MAX, group=group)
+    width = int(width.item())
+    payload = torch.full((n_local_max, width + 1), float('nan'), dtype=torch.float32, device=dev)
+    for i, v in enumerate(vectors):
+        payload[i, 0] = float(v.numel())
+        payload[i, 1:1 + v.numel()] = v.to(torch.float32).reshape(-1)
+    gathered = [torch.empty_like(payload) for _ in range(world)]
+    dist.all_gather(gathered, payload, group=group)
+    out = [None] * n_units
+    for r in range(world):
+        for i, u in enumerate(shard_indices(n_units, r, world)):
+            n = int(gathered[r][i, 0].item())
+            out[u] = gathered[r][i, 1:1 + n].clone()
+    return out

@@ -207,6 +207,21 @@ class MappingWindows:
     def converged(self):
         return self.win_state[:, 3] != 0
 
+    def result_vectors(self):
+        """One flat float32 vector per window -- [frame poses (F*16) | seeds of its keyframes | brightness terms (F*2,
+        if any) | loss] -- the payload of the final cross-rank gather (`shard.gather_ragged`)."""
+        lay, out = self.layout, []
+        for w in range(self.n_windows):
+            f0, f1 = int(lay['win_frame_off'][w]), int(lay['win_frame_off'][w + 1])
+            k0 = int(lay['frame_seg_off'][f0])
+            k1 = int(lay['frame_seg_off'][f1 - 1]) + int(lay['frame_seg_cnt'][f1 - 1])
+            parts = [self.frame_T[f0:f1].reshape(-1), self.k[k0:k1]]
+            if self.frame_aff is not None:
+                parts.append(self.frame_aff[f0:f1].reshape(-1))
+            parts.append(self.win_state[w, 1:2])
+            out.append(torch.cat(parts))
+        return out
+
     def algorithmic_bytes_per_iter(self):
         """SURVEY.md section 8(d) summed over the edges: 24 P + 12 Hl Wl + outputs per edge."""
         total = 0

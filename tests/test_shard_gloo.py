@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from super_primitive_b200.shard import gather_results, owner_of, shard_indices
+from super_primitive_b200.shard import gather_ragged, gather_results, owner_of, shard_indices
 
 
 def test_round_robin_partition():
@@ -57,3 +57,41 @@ def test_gather_world2(n_units):
             assert np.allclose(K[u, :n], np.arange(n) + 10 * u)
             assert np.all(np.isnan(K[u, n:]))
             assert Cst[u] == pytest.approx(0.5 * u)
+
+
+def _ragged_worker(rank, world, port, n_units, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # unit u (a mapping window) has a result of 5 + 3 * (u % 3) floats
+        vecs = [torch.arange(5 + 3 * (u % 3), dtype=torch.float32) + 100 * u for u in shard_indices(n_units, rank, world)]
+        out = gather_ragged(vecs, n_units)
+        q.put((rank, [o.numpy() for o in out]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_units", [3, 6])
+def test_gather_ragged_world2(n_units):
+    """Mapping windows have window-dependent result lengths: NaN-padded rows + lengths, one all-gather."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ragged_worker, args=(r, world, 29700 + n_units, n_units, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, vecs in outs:
+        assert len(vecs) == n_units
+        for u, v in enumerate(vecs):
+            assert np.array_equal(v, np.arange(5 + 3 * (u % 3), dtype=np.float32) + 100 * u)
+
+
+def test_gather_ragged_single_process_is_identity():
+    vecs = [torch.arange(3.0), torch.arange(5.0)]
+    out = gather_ragged(vecs, 2)
+    assert all(torch.equal(a, b) for a, b in zip(out, vecs))
