@@ -47,3 +47,19 @@ def install_pyramid():
     mod = importlib.import_module(f"{__name__}.pyramid")
     ref_mod.keyframe_pyramid = mod.keyframe_pyramid
     return mod
+
+
+def install_image_tt():
+    """Replace ``tool.etc.image_tt`` (tool/etc.py:37-40; the frame hand-over of frontend/process_frame.py) of the
+    already importable reference with the device-side conversion: the 8-bit frame is uploaded (3 bytes per pixel
+    instead of 12) and divided by 255 on the device -- bit-identical output.  Modules that did
+    ``from tool.etc import image_tt`` before this call keep the reference's function; patch them as well by passing
+    them in ``also`` (e.g. ``frontend.process_frame``)."""
+    import importlib
+    ref_mod = importlib.import_module("tool.etc")
+    mod = importlib.import_module(f"{__name__}.frames")
+    ref_mod.image_tt = mod.image_tt
+    fp = sys.modules.get("frontend.process_frame")
+    if fp is not None and hasattr(fp, "image_tt"):
+        fp.image_tt = mod.image_tt
+    return mod

@@ -79,6 +79,33 @@ def test_install_as_core_aliases_modules():
         sys.modules.update(saved)
 
 
+def test_install_image_tt_patches_the_reference_helper():
+    import types
+    import super_primitive_b200 as spb
+    from super_primitive_b200 import frames
+    saved = {k: sys.modules.get(k) for k in ("tool", "tool.etc", "frontend", "frontend.process_frame")}
+    try:
+        tool, etc = types.ModuleType("tool"), types.ModuleType("tool.etc")
+        fe, fp = types.ModuleType("frontend"), types.ModuleType("frontend.process_frame")
+        etc.image_tt = fp.image_tt = lambda image, device='cuda': "reference"
+        tool.etc, fe.process_frame = etc, fp
+        sys.modules.update({"tool": tool, "tool.etc": etc, "frontend": fe, "frontend.process_frame": fp})
+        spb.install_image_tt()
+        assert etc.image_tt is frames.image_tt and fp.image_tt is frames.image_tt
+        import inspect
+        assert list(inspect.signature(frames.image_tt).parameters) == ['image', 'device']      # tool/etc.py:37
+        with pytest.raises(AssertionError):
+            frames.image_tt(np.zeros((4, 4, 3), np.float32))          # 8-bit HWC frames only
+        with pytest.raises(RuntimeError):
+            frames.image_tt(np.zeros((4, 4, 3), np.uint8), device="cpu")   # no CPU fallback
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
 def test_signatures_match_reference_call_surface():
     import inspect
     from super_primitive_b200 import dense_optim as do, dense_optim_batch as dob, depth_render as dr, depth_init as di
