@@ -50,16 +50,26 @@ def install_pyramid():
 
 
 def install_image_tt():
-    """Replace ``tool.etc.image_tt`` (tool/etc.py:37-40; the frame hand-over of frontend/process_frame.py) of the
+    """Replace ``tool.etc.image_tt`` (tool/etc.py:37-40; the frame hand-over of frontend/process_frame.py:216,258) of the
     already importable reference with the device-side conversion: the 8-bit frame is uploaded (3 bytes per pixel
-    instead of 12) and divided by 255 on the device -- bit-identical output.  Modules that did
-    ``from tool.etc import image_tt`` before this call keep the reference's function; patch them as well by passing
-    them in ``also`` (e.g. ``frontend.process_frame``)."""
+    instead of 12) and divided by 255 on the device -- bit-identical output.  Calls that ask for a CPU tensor (the SAM
+    pre-resize, frontend/process_frame.py:101) keep running the reference's own function.  ``frontend.process_frame``
+    binds the name at import (``from tool.etc import image_tt``), so it is patched too when already imported."""
     import importlib
+
+    import torch
     ref_mod = importlib.import_module("tool.etc")
     mod = importlib.import_module(f"{__name__}.frames")
-    ref_mod.image_tt = mod.image_tt
+    reference_image_tt = ref_mod.image_tt
+
+    def image_tt(image, device='cuda'):
+        if torch.device(device).type != 'cuda':
+            return reference_image_tt(image, device)
+        return mod.image_tt(image, device)
+
+    image_tt.__wrapped__ = mod.image_tt
+    ref_mod.image_tt = image_tt
     fp = sys.modules.get("frontend.process_frame")
     if fp is not None and hasattr(fp, "image_tt"):
-        fp.image_tt = mod.image_tt
-    return mod
+        fp.image_tt = image_tt
+    return image_tt

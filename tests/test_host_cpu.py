@@ -90,8 +90,9 @@ def test_install_image_tt_patches_the_reference_helper():
         etc.image_tt = fp.image_tt = lambda image, device='cuda': "reference"
         tool.etc, fe.process_frame = etc, fp
         sys.modules.update({"tool": tool, "tool.etc": etc, "frontend": fe, "frontend.process_frame": fp})
-        spb.install_image_tt()
-        assert etc.image_tt is frames.image_tt and fp.image_tt is frames.image_tt
+        hook = spb.install_image_tt()
+        assert etc.image_tt is hook and fp.image_tt is hook and hook.__wrapped__ is frames.image_tt
+        assert hook(np.zeros((4, 4, 3), np.uint8), 'cpu') == "reference"     # the SAM pre-resize keeps the reference's path
         import inspect
         assert list(inspect.signature(frames.image_tt).parameters) == ['image', 'device']      # tool/etc.py:37
         with pytest.raises(AssertionError):
