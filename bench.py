@@ -164,7 +164,8 @@ class HostStaged:
             self.packed_dev.append((p['pack'], p['trg_rgba']))
             self.packed_host.append((p['pack'].cpu().pin_memory(), p['trg_rgba'].cpu().pin_memory()))
         from super_primitive_b200.frames import FrameIngest
-        self.ingest = FrameIngest(problems, batch.geoms)
+        # SPB_E2E_LEAN=1 (tuning visits with a fused-ingest library only): skip the buffers the iteration does not read
+        self.ingest = FrameIngest(problems, batch.geoms, lean=bool(os.environ.get("SPB_E2E_LEAN")))
         self.arena = self.ingest.host_arena()          # pinned arena a loader decodes the 8-bit frames into
         for i, p in enumerate(problems):
             self.ingest.fill(self.arena, i, p['src_u8'].cpu(), p['trg_u8'].cpu())

@@ -356,7 +356,8 @@ int spb_segment_reinit(const SpbGeom* geom, const float* est_depth, int mode, fl
 /* points per tile the library was built with (SPB_TILE): the host sizes tile tables and level buffers with it */
 int spb_tile_points(void);
 
-/* version / build info */
+/* version / build info: version % 1000 = ABI revision; version / 1000 = bit mask of build-time experiment switches
+ * (0 for the default library; 1 = fused source ingest) */
 int spb_version(void);
 
 #ifdef __cplusplus

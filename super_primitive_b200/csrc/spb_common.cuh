@@ -4,6 +4,12 @@
 #include <stdint.h>
 #include "../../include/spb200.h"
 
+// build-time experiment switches (scripts/build_variant.sh); the default library is built with all of them off and
+// reports them through spb_version() (thousands digit)
+#ifndef SPB_INGEST_FUSED
+#define SPB_INGEST_FUSED 0
+#endif
+
 #define SPB_WARPS 8
 #define SPB_THREADS (SPB_WARPS * 32)
 #define SPB_PPT (SPB_TILE / 32)   // points per lane per tile

@@ -87,6 +87,58 @@ __global__ void k_ingest_pack(const SpbGeom* __restrict__ geoms, const SpbFrameJ
     }
 }
 
+// SPB_INGEST_FUSED (spb_common.cuh, default 0) -- EXPERIMENT, not yet measured (round-2 plan): the
+// source half of the ingest is ONE kernel that samples the 8-bit source frame and writes the tile pack directly
+#if SPB_INGEST_FUSED
+// One warp per tile: header + uv + logd as k_ingest_pack, and the three colour arrays computed on the fly with the
+// arithmetic of k_ingest_sample from taps converted with u8_unit -- the planar float frame and the [3][n_pad] sample
+// array are not needed on this path (written only when the job supplies them), 22 MB instead of 45 MB per 640x480 pair.
+__global__ void k_ingest_fused(const SpbGeom* __restrict__ geoms, const SpbFrameJob* __restrict__ jobs) {
+    const SpbFrameJob jb = jobs[blockIdx.y];
+    if (!jb.src_u8 || !jb.pack) return;
+    const SpbGeom g = geoms[jb.geom];
+    const int lane = threadIdx.x & 31;
+    const int Hl = jb.Hl, Wl = jb.Wl;
+    const float tiw = 2.0f * (1.0f / (float)(g.W - 1));
+    const float tih = 2.0f * (1.0f / (float)(g.H - 1));
+    const float sx = 0.5f * (float)(Wl - 1), sy = 0.5f * (float)(Hl - 1);
+    const uint32_t* lu = reinterpret_cast<const uint32_t*>(g.logd);
+    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < g.n_tiles; t += gridDim.x * (blockDim.x >> 5)) {
+        const int4 td = reinterpret_cast<const int4*>(g.tiles)[t];
+        uint32_t* o = jb.pack + (size_t)t * SPB_PACK_WORDS;
+        if (lane < 4) o[lane] = lane == 0 ? (uint32_t)td.x : (lane == 1 ? (uint32_t)td.z : (lane == 2 ? (uint32_t)td.w : 0u));
+        for (int i = lane; i < SPB_TILE; i += 32) {
+            const bool on = i < td.z;
+            const size_t p = (size_t)td.y + (on ? i : 0);
+            const uint32_t w = g.uv[p];
+            float val[3] = {0.f, 0.f, 0.f};
+            if (on) {
+                const float u = (float)(w & 0xffffu), v = (float)((w >> 16) & 0x7fffu);
+                const float ix = (fmaf(u, tiw, -1.0f) + 1.0f) * sx;
+                const float iy = (fmaf(v, tih, -1.0f) + 1.0f) * sy;
+                const float fxf = floorf(ix), fyf = floorf(iy);
+                const int x0 = (int)fxf, y0 = (int)fyf;
+                const float fx = ix - fxf, fy = iy - fyf;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    auto tap = [&](int x, int y) -> float {
+                        return (x < 0 || y < 0 || x >= Wl || y >= Hl) ? 0.f : u8_unit(jb.src_u8[3 * ((size_t)y * Wl + x) + ch]);
+                    };
+                    float d0, d1;
+                    blend(tap(x0, y0), tap(x0 + 1, y0), tap(x0, y0 + 1), tap(x0 + 1, y0 + 1), fx, fy, val[ch], d0, d1);
+                    if (jb.src_rgb) jb.src_rgb[(size_t)ch * g.n_pad + p] = val[ch];
+                }
+            }
+            o[4 + i] = on ? w : 0u;
+            o[4 + SPB_TILE + i] = on ? lu[p] : 0u;
+            o[4 + 2 * SPB_TILE + i] = on ? __float_as_uint(val[0]) : 0u;
+            o[4 + 3 * SPB_TILE + i] = on ? __float_as_uint(val[1]) : 0u;
+            o[4 + 4 * SPB_TILE + i] = on ? __float_as_uint(val[2]) : 0u;
+        }
+    }
+}
+#endif
+
 extern "C" int spb_ingest_u8(const SpbGeom* geoms, const SpbFrameJob* jobs, int n_jobs, int max_pixels, int max_pad,
                              int max_tiles, void* stream) {
     if (!geoms || !jobs || n_jobs < 1 || max_pixels < 1 || max_pad < 1 || max_tiles < 1) return SPB_EINVAL;
@@ -101,10 +153,16 @@ extern "C" int spb_ingest_u8(const SpbGeom* geoms, const SpbFrameJob* jobs, int 
     };
     k_ingest_frames<<<dim3(gx(256, max_pixels), n_jobs), 256, 0, st>>>(jobs);
     SPB_CHECK_LAUNCH();
+#if SPB_INGEST_FUSED
+    (void)max_pad;
+    k_ingest_fused<<<dim3(gx(8, max_tiles), n_jobs), 256, 0, st>>>(geoms, jobs);
+    SPB_CHECK_LAUNCH();
+#else
     k_ingest_sample<<<dim3(gx(256, max_pad), n_jobs), 256, 0, st>>>(geoms, jobs);
     SPB_CHECK_LAUNCH();
     k_ingest_pack<<<dim3(gx(8, max_tiles), n_jobs), 256, 0, st>>>(geoms, jobs);
     SPB_CHECK_LAUNCH();
+#endif
     return SPB_OK;
 }
 

@@ -43,8 +43,13 @@ class FrameIngest:
     (`host_arena`) that a loader decodes into -- so a chunk of pairs is ONE host->device copy (`upload`) followed by
     the three launches of `spb_ingest_u8` (`run`)."""
 
-    def __init__(self, problems, geoms):
+    def __init__(self, problems, geoms, lean=False):
+        """``lean``: do not materialise the planar float source frame and the [3][n_pad] sample array (only the
+        statistics path reads them).  Needs a library built with the fused source ingest (experiment switch,
+        ``spb_version() // 1000 & 1``); the default library derives the tile pack from those two buffers."""
         import ctypes as C
+        if lean and not (nat.lib().spb_version() // 1000) & 1:
+            raise RuntimeError("FrameIngest(lean=True) needs a library built with -DSPB_INGEST_FUSED=1")
         dev = problems[0]['trg_rgba'].device
         gidx = {id(g): i for i, g in enumerate(geoms)}
         self.n = len(problems)
@@ -66,8 +71,10 @@ class FrameIngest:
             pl = torch.empty((3, Hl, Wl), dtype=torch.float32, device=dev)
             self.src_planar.append(pl)
             j = jarr[i]
-            j.src_u8, j.trg_u8, j.src_planar = self.stage.data_ptr() + so, self.stage.data_ptr() + to, pl.data_ptr()
-            j.src_rgb, j.pack, j.trg_rgba = p['src_rgb'].data_ptr(), p['pack'].data_ptr(), p['trg_rgba'].data_ptr()
+            j.src_u8, j.trg_u8 = self.stage.data_ptr() + so, self.stage.data_ptr() + to
+            j.src_planar = None if lean else pl.data_ptr()
+            j.src_rgb = None if lean else p['src_rgb'].data_ptr()
+            j.pack, j.trg_rgba = p['pack'].data_ptr(), p['trg_rgba'].data_ptr()
             j.geom, j.Hl, j.Wl = gidx[id(g)], Hl, Wl
             self.max_pixels = max(self.max_pixels, Hl * Wl)
             self.max_pad = max(self.max_pad, g.P_pad)
