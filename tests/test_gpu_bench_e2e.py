@@ -27,9 +27,20 @@ def test_image_tt_is_bit_identical_to_the_reference_helper():
         image_tt(torch.zeros((4, 4, 3)), "cuda:0")
 
 
-@pytest.mark.parametrize("mode", ["u8", "raw"])
-def test_frame_upload_rebuilds_identical_buffers_and_results(mode):
+@pytest.mark.parametrize("mode", ["u8", "raw", "u8-lean"])
+def test_frame_upload_rebuilds_identical_buffers_and_results(mode, monkeypatch):
     import bench
+    from super_primitive_b200 import _native as nat
+    if mode == "u8-lean":
+        # experiment builds only (-DSPB_INGEST_FUSED=1, selected with SPB200_LIB): the tile pack is derived straight from
+        # the 8-bit source frame, the planar float frame and the sample array are not materialised
+        if not (nat.lib().spb_version() // 1000) & 1:
+            pytest.skip("default library: no fused source ingest")
+        monkeypatch.setenv("SPB_E2E_LEAN", "1")
+        mode = "u8"
+        lean = True
+    else:
+        lean = False
     dev = torch.device("cuda:0")
     saved = dict(bench.WORKLOAD)
     bench.WORKLOAD.update(H=96, W=128, N=8)
@@ -65,7 +76,7 @@ def test_frame_upload_rebuilds_identical_buffers_and_results(mode):
         assert torch.equal(hs.o_pose, want_pose.cpu()) and torch.equal(hs.o_k, want_k.cpu())
         assert hs.h2d["raw"] == sum(2 * 3 * 96 * 128 * 4 for _ in problems) + hs.params_bytes
         assert hs.h2d["u8"] == sum(2 * 3 * 96 * 128 for _ in problems) + hs.params_bytes
-        if mode == "u8":                  # the float frames themselves were rebuilt too (source planar copy)
+        if mode == "u8" and not lean:     # the float frames themselves were rebuilt too (source planar copy)
             for p, pl in zip(problems, hs.ingest.src_planar):
                 # the reference converts on the HOST (tool/etc.py:37-40); torch's CUDA division by a scalar multiplies by
                 # the reciprocal and differs in the last bit
