@@ -212,3 +212,48 @@ def test_host_early_stop_freezes_the_window(host):
                                 lrs['lr_k'], lrs['lr_aff'], 0.9, 0.999, 1e-8, tol)
     assert hw.win_state[0, 3] == 1.0 and hw.win_state[0, 0] == want['steps']
     np.testing.assert_allclose(hw.k[3:6], want['k'][1].numpy(), atol=1e-6)
+
+
+def _golden_window():
+    z = np.load(os.path.join(HERE, "golden", "mapping_window.npz"))
+    shape = {key[6:]: z[key].item() for key in z.files if key.startswith("shape_")}
+    return z, syn.mapping_window(**shape), shape
+
+
+def test_mapping_oracle_is_pinned_to_the_reference_caller():
+    """tests/golden/mapping_window.npz holds what the reference's OWN `Odometery.mapping` (odometery/odometery.py:687-967,
+    run unmodified with only lietorch stubbed, tests/golden/make_golden_callers.py) leaves after 8 iterations of a
+    3-keyframe window: oracle/window_loop.py must reproduce it bit for bit."""
+    from oracle import window_loop as wl
+    z, w, shape = _golden_window()
+    lr = z["lr"]
+    got = wl.mapping_adam(w['frames'], w['edges'], int(z["iters"]), lr_pose=float(lr[0]), lr_k=float(lr[1]),
+                          lr_aff=float(lr[2]), stop_tol=float(z["stop_tol"]))
+    assert got['steps'] == int(z["iters"])
+    for f in range(len(w['frames'])):
+        assert np.array_equal(got['T'][f].numpy(), z["T"][f]), f"pose of frame {f}"
+        if not np.isnan(z["aff"][f]).any():
+            assert np.array_equal(got['aff'][f].numpy(), z["aff"][f]), f"brightness of frame {f}"
+        if f < shape['n_kf']:
+            assert np.array_equal(got['k'][f].numpy(), z["k"][f]), f"seeds of frame {f}"
+    # the fixture is not trivial: every optimised pose moved by ~ lr_pose * iterations, the first keyframe's did not
+    assert np.array_equal(z["T"][0], w['frames'][0]['T'].numpy())
+    assert 5e-4 < np.abs(z["T"][1] - w['frames'][1]['T'].numpy()).max() < 1e-3
+    assert np.abs(z["k"][0] - w['frames'][0]['k'].numpy()).max() > 5e-2      # window not full: first keyframe's seeds move
+
+
+def test_host_window_update_matches_the_reference_caller_golden(host):
+    """The kernel's arithmetic (host build) with port gradients against the reference's own mapping() result."""
+    z, w, shape = _golden_window()
+    lr = z["lr"]
+    hw = HostWindows([w])
+    host.window_poses_host(C.byref(hw.c))
+    for _ in range(int(z["iters"])):
+        hw.edge_gradients()
+        host.window_update_host(C.byref(hw.c), hw.out_pair.ctypes.data, hw.out_gk.ctypes.data, float(lr[0]), float(lr[1]),
+                                float(lr[2]), 0.9, 0.999, 1e-8, float(z["stop_tol"]))
+    assert hw.win_state[0, 0] == int(z["iters"]) and hw.win_state[0, 3] == 0.0
+    np.testing.assert_allclose(hw.frame_T.reshape(-1, 4, 4), z["T"], atol=2e-7)
+    np.testing.assert_allclose(hw.k.reshape(shape['n_kf'], -1), z["k"], atol=2e-6)
+    ok = ~np.isnan(z["aff"]).any(axis=1)
+    np.testing.assert_allclose(hw.frame_aff[ok], z["aff"][ok], atol=2e-7)
