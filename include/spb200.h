@@ -357,7 +357,7 @@ int spb_segment_reinit(const SpbGeom* geom, const float* est_depth, int mode, fl
 int spb_tile_points(void);
 
 /* version / build info: version % 1000 = ABI revision; version / 1000 = bit mask of build-time experiment switches
- * (0 for the default library; 1 = fused source ingest) */
+ * (0 for the default library; 1 = fused source ingest, 2 = constant-bank context in gradient mode) */
 int spb_version(void);
 
 #ifdef __cplusplus

@@ -385,7 +385,18 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
 #ifndef SPB_PACK_EVICT
 #define SPB_PACK_EVICT 0                        // 1: evict-first L2 hint on the tile-stream copies
 #endif
-template <int MODE, int NP, bool AFF>
+#if SPB_CTX_CONST
+// EXPERIMENT (default off, unmeasured; SASS inspected offline: the gradient kernel's loop goes from 145 instructions with 12
+// LDS to 137 with 5 LDS + 5 LDC).  The per-pair context as a module-global constant array: one launch (k_fill_pair_ctx) folds pose / intrinsics / affine
+// of every pair into global scratch, cudaMemcpyToSymbolAsync moves it here (driver-managed coherence of the constant
+// cache), and the fused kernel's context reads become LDC through the constant cache instead of ~10 broadcast LDS per
+// 32 points on the L1 LSU data pipe (74.7 % busy in gradient mode, profiles/README.md).  One symbol per module: launches
+// that use it must be ordered on one stream.
+#define SPB_CTX_MAXPAIRS 256
+__constant__ float c_pair_ctx[SPB_CTX_MAXPAIRS][F_N];
+#endif
+
+template <int MODE, int NP, bool AFF, bool CTXC = false>
 __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair& pr, float irls_eps,
                                                 float* __restrict__ part_pair, float* __restrict__ part_seg) {
     constexpr int NACC = Sizes<MODE, NP>::NACC;
@@ -398,7 +409,9 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     uint32_t* ring = s_dyn + warp * (SPB_WSTAGES * SPB_SLOT_WORDS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + SPB_WARPS * SPB_WSTAGES * SPB_SLOT_WORDS) + warp * SPB_WSTAGES;
 
-    if (threadIdx.x < 32) fill_fast_ctx(s_ctx, pr, g.K, g.H, g.W);
+    if constexpr (!CTXC) {
+        if (threadIdx.x < 32) fill_fast_ctx(s_ctx, pr, g.K, g.H, g.W);
+    }
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < SPB_WSTAGES; ++s) mbar_init(smem_u32(bars + s), 1);
@@ -407,7 +420,11 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     const int nshift = min(g.n_seg, SPB_NSHIFT);
     for (int b = threadIdx.x; b < nshift; b += blockDim.x) s_shift[b] = __ldg(pr.k + b) - __ldg(g.seg_lkp + b);
     __syncthreads();
+#if SPB_CTX_CONST
+    const float* c = CTXC ? c_pair_ctx[blockIdx.y] : s_ctx;
+#else
     const float* c = s_ctx;
+#endif
 
 #if SPB_CTA_CONTIG
     // every CTA owns one contiguous run of tiles, its warps march through it side by side
@@ -577,6 +594,36 @@ k_align_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pa
     float* base = work + pair * work_stride;
     align_body_warp<MODE, NP, AFF>(s_g, s_pr, irls_eps, base, base + (size_t)gridDim.x * NACC);
 }
+
+#if SPB_CTX_CONST
+__global__ void k_fill_pair_ctx(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs, int n_pairs,
+                                float* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const SpbPair pr = pairs[p];
+    const SpbGeom& g = geoms[pr.geom];
+    float* s = out + (size_t)p * F_N;
+    for (int i = 0; i < F_N; ++i) s[i] = 0.f;
+    fill_fast_ctx_serial(s, pr, g.K, g.H, g.W);
+}
+
+template <int MODE, int NP, bool AFF>
+__global__ void __launch_bounds__(SPB_THREADS, Occ<MODE, NP>::CTAS)
+k_align_global_cc(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs, float irls_eps,
+                  float* __restrict__ work, int64_t work_stride) {
+    constexpr int NACC = Sizes<MODE, NP>::NACC;
+    const int pair = blockIdx.y;
+    __shared__ SpbPair s_pr;
+    __shared__ SpbGeom s_g;
+    if (threadIdx.x == 0) {
+        s_pr = pairs[pair];
+        s_g = geoms[s_pr.geom];
+    }
+    __syncthreads();
+    float* base = work + pair * work_stride;
+    align_body_warp<MODE, NP, AFF, true>(s_g, s_pr, irls_eps, base, base + (size_t)gridDim.x * NACC);
+}
+#endif
 
 // Fixed-order sum over the per-CTA partials [ctas][NACC] (contiguous): the block's threads form R = blockDim / NACC
 // row groups; thread (r, c) adds rows r, r + R, ... of column c (consecutive threads read consecutive floats, 8 loads
@@ -1086,17 +1133,29 @@ k_grad_finalize_adam(const SpbGeom* __restrict__ geoms, const SpbPair* __restric
     adam_update_body(out_pair, out_gk, seg_off, seg_cnt, with_affine, h, poses, k, aff_trg, adam_pair, adam_seg);
 }
 
-extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, int n_pairs,
-                                   int max_tiles, int with_affine, float* work, int64_t work_stride, float* out_pair,
-                                   float* out_gk, void* ev_before, void* ev_after, void* stream) {
-    if (!geoms || !pairs || !seg_off || n_pairs < 1 || max_tiles < 1 || !work || !out_pair || !out_gk)
-        return SPB_EINVAL;
-    if (n_pairs > 65535) return SPB_ELIMIT;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int ctas = ctas_grad(max_tiles, n_pairs);
-    if (work_stride < (int64_t)ctas * SPB_PAIR_NOUT + max_tiles) return SPB_EINVAL;
+// the fused gradient-mode launch of the batched entry points
+static int launch_grad_align(const SpbGeom* geoms, const SpbPair* pairs, int n_pairs, int ctas, int with_affine,
+                             float* work, int64_t work_stride, cudaStream_t st) {
     dim3 grid(ctas, n_pairs);
-    if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
+#if SPB_CTX_CONST
+    if (n_pairs <= SPB_CTX_MAXPAIRS && (int64_t)n_pairs * work_stride >= (int64_t)n_pairs * F_N) {
+        // context of every pair -> scratch at the front of `work` (overwritten by the partials afterwards) -> constant array
+        k_fill_pair_ctx<<<(n_pairs + 63) / 64, 64, 0, st>>>(geoms, pairs, n_pairs, work);
+        SPB_CHECK_LAUNCH();
+        cudaError_t e = cudaMemcpyToSymbolAsync(c_pair_ctx, work, (size_t)n_pairs * F_N * sizeof(float), 0,
+                                                cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+        if (with_affine) {
+            if ((e = allow_dyn_smem(k_align_global_cc<MODE_GRAD, 6, true>)) != cudaSuccess) return (int)e;
+            k_align_global_cc<MODE_GRAD, 6, true><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
+        } else {
+            if ((e = allow_dyn_smem(k_align_global_cc<MODE_GRAD, 6, false>)) != cudaSuccess) return (int)e;
+            k_align_global_cc<MODE_GRAD, 6, false><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
+        }
+        SPB_CHECK_LAUNCH();
+        return SPB_OK;
+    }
+#endif
     if (with_affine) {
         cudaError_t e = allow_dyn_smem(k_align_global<MODE_GRAD, 6, true>);
         if (e != cudaSuccess) return (int)e;
@@ -1107,6 +1166,23 @@ extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, c
         k_align_global<MODE_GRAD, 6, false><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
     }
     SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+extern "C" int spb_grad_accumulate(const SpbGeom* geoms, const SpbPair* pairs, const int32_t* seg_off, int n_pairs,
+                                   int max_tiles, int with_affine, float* work, int64_t work_stride, float* out_pair,
+                                   float* out_gk, void* ev_before, void* ev_after, void* stream) {
+    if (!geoms || !pairs || !seg_off || n_pairs < 1 || max_tiles < 1 || !work || !out_pair || !out_gk)
+        return SPB_EINVAL;
+    if (n_pairs > 65535) return SPB_ELIMIT;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = ctas_grad(max_tiles, n_pairs);
+    if (work_stride < (int64_t)ctas * SPB_PAIR_NOUT + max_tiles) return SPB_EINVAL;
+    if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
+    {
+        const int rc = launch_grad_align(geoms, pairs, n_pairs, ctas, with_affine, work, work_stride, st);
+        if (rc != SPB_OK) return rc;
+    }
     if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
     k_finalize_grad_global<<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, ctas, work, work_stride, out_pair, out_gk);
     SPB_CHECK_LAUNCH();
@@ -1133,18 +1209,11 @@ extern "C" int spb_adam_iterate(const SpbGeom* geoms, const SpbPair* pairs, cons
     cudaStream_t st = (cudaStream_t)stream;
     const int ctas = ctas_grad(max_tiles, n_pairs);
     if (work_stride < (int64_t)ctas * SPB_PAIR_NOUT + max_tiles) return SPB_EINVAL;
-    dim3 grid(ctas, n_pairs);
     if (ev_before) cudaEventRecord((cudaEvent_t)ev_before, st);
-    if (with_affine) {
-        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GRAD, 6, true>);
-        if (e != cudaSuccess) return (int)e;
-        k_align_global<MODE_GRAD, 6, true><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
-    } else {
-        cudaError_t e = allow_dyn_smem(k_align_global<MODE_GRAD, 6, false>);
-        if (e != cudaSuccess) return (int)e;
-        k_align_global<MODE_GRAD, 6, false><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
+    {
+        const int rc = launch_grad_align(geoms, pairs, n_pairs, ctas, with_affine, work, work_stride, st);
+        if (rc != SPB_OK) return rc;
     }
-    SPB_CHECK_LAUNCH();
     if (ev_after) cudaEventRecord((cudaEvent_t)ev_after, st);
     const SpbAdamHyper h{lr_pose, lr_k, lr_aff, beta1, beta2, eps};
     k_grad_finalize_adam<<<n_pairs, 256, 0, st>>>(geoms, pairs, seg_off, seg_cnt, ctas, work, work_stride, out_pair, out_gk,

@@ -7,8 +7,11 @@
 // build-time experiment switches (scripts/build_variant.sh); the default library is built with all of them off and
 // reports them through spb_version() (thousands digit)
 #ifndef SPB_INGEST_FUSED
-#define SPB_INGEST_FUSED 0
+#define SPB_INGEST_FUSED 0                      // 1: fused source ingest (spb_ingest.cu)
 #endif
+#ifndef SPB_CTX_CONST
+#define SPB_CTX_CONST 0                         // 1: gradient mode of the batched solver reads the per-pair context from a
+#endif                                          //    __constant__ array (spb_align.cu)
 
 #define SPB_WARPS 8
 #define SPB_THREADS (SPB_WARPS * 32)

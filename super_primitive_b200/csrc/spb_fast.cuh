@@ -122,6 +122,35 @@ __device__ __forceinline__ void fill_fast_ctx(float* s, const SpbPair& pr, const
     }
 }
 
+#if SPB_CTX_CONST
+// one thread writes the whole context (constant-context experiment, spb_align.cu): fill_fast_ctx's two halves in turn
+__device__ __forceinline__ void fill_fast_ctx_serial(float* s, const SpbPair& pr, const float* Ksrc, int H, int W) {
+    const float ifx = 1.0f / Ksrc[0], ify = 1.0f / Ksrc[4];
+    for (int i = 0; i < 3; ++i) {
+        s[F_MAT(i, 0)] = pr.pose[4 * i] * ifx;
+        s[F_MAT(i, 1)] = pr.pose[4 * i + 1] * ify;
+        s[F_MAT(i, 2)] = pr.pose[4 * i + 2];
+        s[F_TR(i)] = pr.pose[4 * i + 3];
+    }
+    s[F_CX] = Ksrc[2];
+    s[F_CY] = Ksrc[5];
+    const float tiw = 2.0f * (1.0f / (float)(W - 1)), tih = 2.0f * (1.0f / (float)(H - 1));
+    const float sx = 0.5f * (float)(pr.Wl - 1), sy = 0.5f * (float)(pr.Hl - 1);
+    const float fxt = pr.K_trg[0], fyt = pr.K_trg[4], cxt = pr.K_trg[2], cyt = pr.K_trg[5];
+    float a = 0.f, b = 0.f;
+    if (pr.aff_src != nullptr && pr.aff_trg != nullptr) {
+        a = pr.aff_trg[0] - pr.aff_src[0];
+        b = pr.aff_trg[1] - pr.aff_src[1];
+    }
+    const float ea = expf(-a);
+    s[F_AX] = fxt * tiw; s[F_BX] = fmaf(cxt, tiw, -1.0f);
+    s[F_AY] = fyt * tih; s[F_BY] = fmaf(cyt, tih, -1.0f);
+    s[F_SX] = sx; s[F_SY] = sy; s[F_TAU] = pr.tau; s[F_EA] = ea; s[F_BB] = b;
+    const float cu = -ea * (sx * tiw) * fxt, cv = -ea * (sy * tih) * fyt;
+    s[F_CU] = cu; s[F_CV] = cv; s[F_CUU] = cu * cu; s[F_CUV] = cu * cv; s[F_CUV2] = cu * cv; s[F_CVV] = cv * cv;
+}
+#endif
+
 // geometry shared by both modes: returns validity, fills the projected quantities
 struct Proj {
     float Yx, Yy, Yz, rho, xb, yb, fx, fy, zs;   // zs = z of the source point
