@@ -73,3 +73,39 @@ def tracker_adam(src, trg, k0, pose0, iters, lr_pose=1e-2, lr_k=1e-3, lr_aff=5e-
                 'costs': costs}
     finally:
         torch.set_grad_enabled(was)
+
+
+def sfm_adam(src_levels, trg_levels, k0, T0s, iters_per_level, lr_k=1e-3, lr_pose=1e-2, cost_config=None):
+    """The two-frame SfM loop, odometery/two_frame_sfm.py:127-206: one source keyframe against `len(T0s)` supporting
+    frames, coarse-to-fine over the pyramid levels (`src_levels[l]`, `trg_levels[j][l]`), `iters_per_level` iterations per
+    level (500 in the reference).  Unlike the tracker, the increment is NOT folded: every pose is `Exp(delta_j) @ T0_j` with
+    `delta_j` accumulating in ONE Adam (seeds lr 1e-3, increments lr 1e-2, :117-121); the very first iteration evaluates the
+    cost but takes no step (`if count > 0`, :201-205); loss = sum_j mean|residual_j|.
+    Returns dict(k, deltas [(6,)...], poses [(4,4)...], losses)."""
+    cfg = cost_config or {'mode': 'colour', 'collect_stats': 0}
+    was = torch.is_grad_enabled()
+    torch.set_grad_enabled(True)
+    try:
+        dt = k0.dtype
+        k = k0.detach().clone().requires_grad_(True)
+        deltas = [torch.zeros(1, 6, dtype=dt, requires_grad=True) for _ in T0s]
+        opt = torch.optim.Adam([{'params': k, 'lr': lr_k}, {'params': deltas, 'lr': lr_pose}], lr=1e-3)
+        losses, count = [], 0
+        for lvl in range(len(src_levels)):
+            for _ in range(iters_per_level):
+                per = []
+                for j, T0 in enumerate(T0s):
+                    pose = exp_se3(deltas[j][0]) @ T0
+                    res = port.cost_single(src_levels[lvl], trg_levels[j][lvl], k, pose, cfg)
+                    per.append(torch.mean(torch.abs(res['residual'])))
+                loss = torch.sum(torch.stack(per))
+                if count > 0:
+                    loss.backward()
+                    opt.step()
+                    opt.zero_grad()
+                count += 1
+                losses.append(float(loss.detach()))
+        return {'k': k.detach(), 'deltas': [d.detach()[0] for d in deltas],
+                'poses': [(exp_se3(d.detach()[0]) @ T0) for d, T0 in zip(deltas, T0s)], 'losses': losses}
+    finally:
+        torch.set_grad_enabled(was)

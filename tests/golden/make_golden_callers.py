@@ -229,6 +229,60 @@ def case_tracker():
     print(f"tracker: wrote {os.path.getsize(path) / 1e3:.0f} kB")
 
 
+SFM = dict(H=48, W=64, N=8, kind="overlap", seed=21, noise=0.01, levels=2, n_supp=2)
+
+
+def case_sfm():
+    """`SfM.run` (odometery/two_frame_sfm.py:127-215) run unmodified -- BASELINE config 0 in miniature: one source
+    keyframe with 8 segments against two supporting frames, 2 pyramid levels x 500 iterations, the reference's Adam
+    (seeds 1e-3, poses 1e-2), poses as `LieGroupParameter`s that are never re-zeroed.  `init_keyframes` /
+    `init_optimisation` (dataset + SAM frontend + random start) are replaced by fixed synthetic state; the GUI queues
+    are inert.  Pins oracle/adam_loop.sfm_adam bit for bit."""
+    import queue
+    import odometery.two_frame_sfm as sfm_mod
+    from image.keyframe import KeyFrame as RefKeyFrame
+    from oracle import adam_loop
+    lt = sys.modules["lietorch"]
+    c = SFM
+    src = syn.make_keyframe(c['H'], c['W'], c['N'], kind=c['kind'], seed=c['seed'], noise=c['noise'])
+    trgs = [syn.make_keyframe(c['H'], c['W'], c['N'], shift=(2.0 + j, 1.0 - 0.5 * j), noise=c['noise'],
+                              seed=c['seed'] + 1 + j, supporting=True) for j in range(c['n_supp'])]
+    T0s = [syn.small_pose(0.02 + 0.01 * j, 0.004, -0.003, 0.003, -0.002 * (j + 1), 0.0015) for j in range(c['n_supp'])]
+    k0 = torch.log(2.0 + 2.0 * torch.rand(c['N'], generator=torch.Generator().manual_seed(c['seed'])))   # :103-105
+    o = object.__new__(sfm_mod.SfM)
+    o.config = {'aligment': {'pyramid_min': 0, 'pyramid_max': c['levels'],
+                             'cost_params': {'normal_loss': 'cosine', 'normal_weight': 0.0, 'depth_median_weight': 0.0}}}
+    o.paused = False
+    o.init_keyframes = lambda: None
+    o.init_optimisation = lambda: None
+    o.kf_queue, o.viz_queue, o.pause_queue = _Queue(), _Queue(), queue.Queue()
+    o.waitev = types.SimpleNamespace(wait=lambda: None)
+    o.src_keyframe = RefKeyFrame(src.image, src.K, src.logdepth_perseg, src.keypoints, src.keypoint_regions)
+    pose_to_mat = lambda x: x.retr().matrix()[0]                                                         # noqa: E731
+    o.supp_frames = [(RefKeyFrame(t.image, t.K), lt.LieGroupParameter(lt.SE3(T0[None].clone())), pose_to_mat)
+                     for t, T0 in zip(trgs, T0s)]
+    o.src_depth_keypoints_opt = torch.nn.Parameter(k0.clone())
+    o.instatiate_optimisation()
+    o.run()
+    torch.set_grad_enabled(True)
+    k_ref = o.src_depth_keypoints_opt.detach()
+    d_ref = [p.detach().as_subclass(torch.Tensor)[0] for _, p, _ in o.supp_frames]
+    src_lv = syn.keyframe_pyramid(src, 0, c['levels'])
+    trg_lv = [syn.keyframe_pyramid(t, 0, c['levels']) for t in trgs]
+    got = adam_loop.sfm_adam(src_lv, trg_lv, k0, T0s, 500)
+    worst = max([float((got['k'] - k_ref).abs().max())] + [float((a - b).abs().max()) for a, b in zip(got['deltas'], d_ref)])
+    print(f"oracle vs reference SfM.run(): max |d| = {worst:.3e} (seeds moved by {float((k_ref - k0).abs().max()):.3e}, "
+          f"increments up to {max(float(d.abs().max()) for d in d_ref):.3e})")
+    assert worst == 0.0, worst
+    store = dict(k0=k0.numpy(), k=k_ref.numpy(), deltas=np.stack([d.numpy() for d in d_ref]),
+                 T0s=np.stack([T.numpy() for T in T0s]), loss_first=got['losses'][0], loss_last=got['losses'][-1],
+                 **{"cfg_" + key: np.array(val) for key, val in c.items()})
+    path = os.path.join(HERE, "sfm_run.npz")
+    np.savez_compressed(path, **store)
+    print(f"sfm_run: wrote {os.path.getsize(path) / 1e3:.0f} kB; loss {got['losses'][0]:.5f} -> {got['losses'][-1]:.5f}")
+
+
 if __name__ == "__main__":
     main()
     case_tracker()
+    case_sfm()

@@ -34,3 +34,22 @@ def test_tracker_oracle_is_pinned_to_the_reference_caller():
     np.testing.assert_allclose(np.linalg.inv(z["frame_pose"].astype(np.float64)) @ z["kf_pose"], z["rel_pose"], atol=1e-6)
     assert np.abs(z["rel_pose"] - pose0.numpy()).max() > 3 * c['lr']
     assert len(got['costs']) == c['iters'] and all(math.isfinite(x) for x in got['costs'])
+
+
+def test_sfm_oracle_is_pinned_to_the_reference_caller():
+    """odometery/two_frame_sfm.py:127-215 (BASELINE config 0 in miniature): 2 pyramid levels x 500 iterations, one source
+    keyframe against two supporting frames, poses as never-re-zeroed increments, first iteration without a step."""
+    from oracle import adam_loop
+    z = np.load(os.path.join(HERE, "golden", "sfm_run.npz"))
+    c = {key[4:]: z[key].item() for key in z.files if key.startswith("cfg_")}
+    src = syn.make_keyframe(c['H'], c['W'], c['N'], kind=c['kind'], seed=c['seed'], noise=c['noise'])
+    trgs = [syn.make_keyframe(c['H'], c['W'], c['N'], shift=(2.0 + j, 1.0 - 0.5 * j), noise=c['noise'],
+                              seed=c['seed'] + 1 + j, supporting=True) for j in range(c['n_supp'])]
+    T0s = [torch.from_numpy(T) for T in z["T0s"]]
+    got = adam_loop.sfm_adam(syn.keyframe_pyramid(src, 0, c['levels']),
+                             [syn.keyframe_pyramid(t, 0, c['levels']) for t in trgs], torch.from_numpy(z["k0"]), T0s, 500)
+    assert np.array_equal(got['k'].numpy(), z["k"])
+    assert np.array_equal(np.stack([d.numpy() for d in got['deltas']]), z["deltas"])
+    assert got['losses'][0] == float(z["loss_first"]) and got['losses'][-1] == float(z["loss_last"])
+    assert got['losses'][-1] < 0.1 * got['losses'][0]                 # the run is a real optimisation, not a no-op
+    assert len(got['losses']) == 500 * c['levels']
