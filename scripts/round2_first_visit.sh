@@ -10,6 +10,8 @@ TAG=${1:-r02a}
 OUT=gpurun_out; mkdir -p $OUT
 B="--no-cpu-baseline --no-e2e"
 L=$PWD/super_primitive_b200/csrc
+[ -f $L/libspb200_cc.so ] || bash scripts/build_variant.sh cc -DSPB_CTX_CONST=1 | tail -1
+[ -f $L/libspb200_fused.so ] || bash scripts/build_variant.sh fused -DSPB_INGEST_FUSED=1 | tail -1
 timeout 200 python bench.py --steps 30 --warmup 5 $B > $OUT/bench_gn_base_$TAG.json 2> $OUT/bench_gn_base_$TAG.err
 for v in cc fused; do
   SPB200_LIB=$L/libspb200_$v.so timeout 300 python -m pytest tests -q -m gpu 2>&1 | tail -30 > $OUT/pytest_${v}_$TAG.log
