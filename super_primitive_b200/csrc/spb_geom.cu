@@ -2,6 +2,7 @@
 // point lifting, depth splat.  All once-per-keyframe / once-per-frame work (not per iteration),
 // all HBM-streaming; grids are sized from the data, loads are coalesced along image rows.
 #include "spb_common.cuh"
+#include "spb_frame_stages.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // compaction pass 1: one warp per (segment,row): popcount of the row
@@ -168,29 +169,9 @@ extern "C" int spb_pack_rgba(const float* planar, int64_t img_stride, int n_img,
 // ------------------------------------------------------------------------------------------------
 __global__ void k_sample_source(const __grid_constant__ SpbGeom g, const float* __restrict__ img, int Hl, int Wl,
                                 float* __restrict__ out) {
-    const float tiw = 2.0f * (1.0f / (float)(g.W - 1));
-    const float tih = 2.0f * (1.0f / (float)(g.H - 1));
-    const float sx = 0.5f * (float)(Wl - 1), sy = 0.5f * (float)(Hl - 1);
-    const size_t HW = (size_t)Hl * Wl;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pad; p += gridDim.x * blockDim.x) {
-        const uint32_t w = g.uv[p];
-        const float u = (float)(w & 0xffffu), v = (float)((w >> 16) & 0x7fffu);
-        const float ix = (fmaf(u, tiw, -1.0f) + 1.0f) * sx;
-        const float iy = (fmaf(v, tih, -1.0f) + 1.0f) * sy;
-        const float fxf = floorf(ix), fyf = floorf(iy);
-        const int x0 = (int)fxf, y0 = (int)fyf;
-        const float fx = ix - fxf, fy = iy - fyf;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float* pl = img + ch * HW;
-            auto tap = [&](int x, int y) -> float {
-                return (x < 0 || y < 0 || x >= Wl || y >= Hl) ? 0.f : pl[(size_t)y * Wl + x];
-            };
-            float val, d0, d1;
-            blend(tap(x0, y0), tap(x0 + 1, y0), tap(x0, y0 + 1), tap(x0 + 1, y0 + 1), fx, fy, val, d0, d1);
-            out[(size_t)ch * g.n_pad + p] = val;
-        }
-    }
+    const SourceSampleScale sc = source_sample_scale(g, Hl, Wl);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pad; p += gridDim.x * blockDim.x)
+        sample_source_point(g, img, Hl, Wl, sc, p, out);
 }
 
 extern "C" int spb_sample_source(const SpbGeom* geom, const float* src_planar, int Hl, int Wl, float* out,
@@ -209,20 +190,7 @@ __global__ void k_build_tile_pack(const __grid_constant__ SpbGeom g, const float
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= g.n_tiles) return;
-    const int4 td = reinterpret_cast<const int4*>(g.tiles)[t];
-    uint32_t* o = pack + (size_t)t * SPB_PACK_WORDS;
-    if (lane < 4) o[lane] = lane == 0 ? (uint32_t)td.x : (lane == 1 ? (uint32_t)td.z : (lane == 2 ? (uint32_t)td.w : 0u));
-    const uint32_t* rgbu = reinterpret_cast<const uint32_t*>(rgb);
-    const uint32_t* lu = reinterpret_cast<const uint32_t*>(g.logd);
-    for (int i = lane; i < SPB_TILE; i += 32) {
-        const bool on = i < td.z;
-        const size_t p = (size_t)td.y + (on ? i : 0);
-        o[4 + i] = on ? g.uv[p] : 0u;
-        o[4 + SPB_TILE + i] = on ? lu[p] : 0u;
-        o[4 + 2 * SPB_TILE + i] = on ? rgbu[p] : 0u;
-        o[4 + 3 * SPB_TILE + i] = on ? rgbu[(size_t)g.n_pad + p] : 0u;
-        o[4 + 4 * SPB_TILE + i] = on ? rgbu[2 * (size_t)g.n_pad + p] : 0u;
-    }
+    build_tile_pack_tile(g, rgb, pack, t, lane);
 }
 
 extern "C" int spb_build_tile_pack(const SpbGeom* geom, const float* src_rgb, uint32_t* pack, void* stream) {

@@ -5,11 +5,13 @@
 // HWC -> CHW; 12 bytes per pixel over PCIe).  Here the 3-byte pixels travel and `image_tt` runs on the device -- the same
 // float32 division, so the frames are bit-identical -- fused with the re-layouts that follow:
 //   k_ingest_frames : target u8 HWC -> RGBA-interleaved float4 (spb_pack_rgba of image_tt), source u8 HWC -> planar CHW float
-//   k_ingest_sample : cached source samples at every point's own pixel (spb_sample_source), grid.y = job
-//   k_ingest_pack   : tile-major level buffer (spb_build_tile_pack), grid.y = job
+//   k_ingest_sample : cached source samples at every point's own pixel, grid.y = job   } the per-item bodies of
+//   k_ingest_pack   : tile-major level buffer, grid.y = job                            } spb_sample_source /
+//                                                                                        spb_build_tile_pack (spb_frame_stages.cuh)
 // Job descriptors and geometries live in DEVICE memory (uploaded once per batch), so a step's ingest is three launches
 // regardless of the number of pairs.  HBM-streaming, coalesced; bandwidth ~45 MB per 640x480 pair.
 #include "spb_common.cuh"
+#include "spb_frame_stages.cuh"
 
 // image_tt arithmetic: float32(u8) / 255.f, IEEE division (torch divides a uint8 tensor by a Python float in float32)
 __device__ __forceinline__ float u8_unit(uint32_t b) { return __fdiv_rn((float)b, 255.0f); }
@@ -32,59 +34,24 @@ __global__ void k_ingest_frames(const SpbFrameJob* __restrict__ jobs) {
     }
 }
 
-// same arithmetic as k_sample_source (spb_geom.cu): bilinear of the source level image at the point's own pixel
+// spb_sample_source for every job: cached source samples at the points' own pixels (spb_frame_stages.cuh)
 __global__ void k_ingest_sample(const SpbGeom* __restrict__ geoms, const SpbFrameJob* __restrict__ jobs) {
     const SpbFrameJob jb = jobs[blockIdx.y];
     if (!jb.src_planar || !jb.src_rgb) return;
     const SpbGeom g = geoms[jb.geom];
-    const int Hl = jb.Hl, Wl = jb.Wl;
-    const float tiw = 2.0f * (1.0f / (float)(g.W - 1));
-    const float tih = 2.0f * (1.0f / (float)(g.H - 1));
-    const float sx = 0.5f * (float)(Wl - 1), sy = 0.5f * (float)(Hl - 1);
-    const size_t HW = (size_t)Hl * Wl;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pad; p += gridDim.x * blockDim.x) {
-        const uint32_t w = g.uv[p];
-        const float u = (float)(w & 0xffffu), v = (float)((w >> 16) & 0x7fffu);
-        const float ix = (fmaf(u, tiw, -1.0f) + 1.0f) * sx;
-        const float iy = (fmaf(v, tih, -1.0f) + 1.0f) * sy;
-        const float fxf = floorf(ix), fyf = floorf(iy);
-        const int x0 = (int)fxf, y0 = (int)fyf;
-        const float fx = ix - fxf, fy = iy - fyf;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float* pl = jb.src_planar + ch * HW;
-            auto tap = [&](int x, int y) -> float {
-                return (x < 0 || y < 0 || x >= Wl || y >= Hl) ? 0.f : pl[(size_t)y * Wl + x];
-            };
-            float val, d0, d1;
-            blend(tap(x0, y0), tap(x0 + 1, y0), tap(x0, y0 + 1), tap(x0 + 1, y0 + 1), fx, fy, val, d0, d1);
-            jb.src_rgb[(size_t)ch * g.n_pad + p] = val;
-        }
-    }
+    const SourceSampleScale sc = source_sample_scale(g, jb.Hl, jb.Wl);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pad; p += gridDim.x * blockDim.x)
+        sample_source_point(g, jb.src_planar, jb.Hl, jb.Wl, sc, p, jb.src_rgb);
 }
 
-// same layout as k_build_tile_pack (spb_geom.cu): one warp per tile, header + five SPB_TILE-word arrays
+// spb_build_tile_pack for every job: one warp per tile (spb_frame_stages.cuh)
 __global__ void k_ingest_pack(const SpbGeom* __restrict__ geoms, const SpbFrameJob* __restrict__ jobs) {
     const SpbFrameJob jb = jobs[blockIdx.y];
     if (!jb.src_rgb || !jb.pack) return;
     const SpbGeom g = geoms[jb.geom];
     const int lane = threadIdx.x & 31;
-    const uint32_t* rgbu = reinterpret_cast<const uint32_t*>(jb.src_rgb);
-    const uint32_t* lu = reinterpret_cast<const uint32_t*>(g.logd);
-    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < g.n_tiles; t += gridDim.x * (blockDim.x >> 5)) {
-        const int4 td = reinterpret_cast<const int4*>(g.tiles)[t];
-        uint32_t* o = jb.pack + (size_t)t * SPB_PACK_WORDS;
-        if (lane < 4) o[lane] = lane == 0 ? (uint32_t)td.x : (lane == 1 ? (uint32_t)td.z : (lane == 2 ? (uint32_t)td.w : 0u));
-        for (int i = lane; i < SPB_TILE; i += 32) {
-            const bool on = i < td.z;
-            const size_t p = (size_t)td.y + (on ? i : 0);
-            o[4 + i] = on ? g.uv[p] : 0u;
-            o[4 + SPB_TILE + i] = on ? lu[p] : 0u;
-            o[4 + 2 * SPB_TILE + i] = on ? rgbu[p] : 0u;
-            o[4 + 3 * SPB_TILE + i] = on ? rgbu[(size_t)g.n_pad + p] : 0u;
-            o[4 + 4 * SPB_TILE + i] = on ? rgbu[2 * (size_t)g.n_pad + p] : 0u;
-        }
-    }
+    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < g.n_tiles; t += gridDim.x * (blockDim.x >> 5))
+        build_tile_pack_tile(g, jb.src_rgb, jb.pack, t, lane);
 }
 
 // SPB_INGEST_FUSED (spb_common.cuh, default 0) -- EXPERIMENT, not yet measured (round-2 plan): the
