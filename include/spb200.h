@@ -290,9 +290,11 @@ int spb_window_iterate(const SpbGeom* geoms, const SpbPair* pairs, const SpbWind
                        double lr_aff, double beta1, double beta2, double eps, double stop_tol, void* ev_before,
                        void* ev_after, void* stream);
 
-/* CTAs per pair the batched launches use for (max_tiles, n_pairs): the workspace stride must be
- * >= ctas * nacc + max_tiles * nseg floats (nacc/nseg = 16/1 gradient, 47/10 GN). */
+/* CTAs per pair the batched launches use for (max_tiles, n_pairs), and the workspace stride (floats per pair) every
+ * batched entry point accepts for them: ctas * (per-CTA accumulators) + max_tiles * (per-tile run record), maxima
+ * over the kernel variants.  Callers size `work` as n_pairs * spb_gn_work_stride(...). */
 int spb_gn_ctas(int max_tiles, int n_pairs);
+int64_t spb_gn_work_stride(int max_tiles, int n_pairs);
 
 /* Damped Schur-complement solve (float64) + SE(3) retraction T <- Exp(xi) T + log-depth update for
  * n_pairs problems, with LM accept/reject bookkeeping kept on the device:

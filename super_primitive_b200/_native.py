@@ -84,6 +84,7 @@ _PROTOS = {
     "spb_workspace_floats": (_i64, [C.POINTER(SpbGeom), _i, _i]),
     "spb_workspace_floats_points": (_i64, [_i]),
     "spb_gn_ctas": (_i, [_i, _i]),
+    "spb_gn_work_stride": (_i64, [_i, _i]),
     "spb_gn_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "spb_gn_iterate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp]),

@@ -230,11 +230,15 @@ __device__ __forceinline__ void eval_point(const float* __restrict__ c, const fl
     }
 }
 
+// per-CTA accumulators (NACC) and per-run partials (NSEG) of each kernel variant.  The 6-column GN variant keeps rows
+// 0..2 of the pose block + g_0..g_3 per run and derives the depth column from them (spb_gn_packed.cuh).
 template <int MODE, int NP>
 struct Sizes {
-    static constexpr int NACC = (MODE == MODE_GRAD) ? SPB_PAIR_NOUT : (NP * (NP + 1) / 2 + NP + 3);
-    static constexpr int NSEG = (MODE == MODE_GRAD) ? 1 : (NP + 2);
+    static constexpr int NACC = (MODE == MODE_GRAD) ? SPB_PAIR_NOUT : (NP == 6 ? 12 : NP * (NP + 1) / 2 + NP + 3);
+    static constexpr int NSEG = (MODE == MODE_GRAD) ? 1 : (NP == 6 ? 19 : NP + 2);
 };
+#define SPB_MAX_NACC 47        // over the variants: 8-column GN
+#define SPB_MAX_NSEG 19        // 6-column GN
 
 // ------------------------------------------------------------------------------------------------
 // Compact-geometry variant.  grid = (ctas_per_pair, n_pairs)
@@ -318,43 +322,76 @@ __device__ __forceinline__ void align_body(const SpbGeom& g, const SpbPair& pr, 
 
 // ------------------------------------------------------------------------------------------------
 // Multi-value warp reduction: N per-lane values -> N warp sums with ~N+2 shuffles instead of 5N.
-// The first 8 values are folded with a butterfly that halves the value set at every exchange
-// (4+2+1 shuffles), then two more exchanges finish the sum; lane 4*i holds the total of value i.
-// Fixed exchange order => deterministic.
+// Values are folded in chunks of K = 16 / 8 / 4 with a butterfly that halves the value set at every exchange
+// (K/2 + K/4 + ... + 1 shuffles), the remaining log2(32/K) exchanges finish the sums; the total of value i of a chunk
+// ends up in lane i * (32/K).  Fixed exchange order => deterministic.
 // ------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void butterfly_store(const float* v, float* __restrict__ dst, int lane) {
+    static_assert(K == 16 || K == 8 || K == 4, "chunk size");
+    float a[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) a[i] = v[i];
+    int n = K;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        if (n > 1) {
+            const bool up = lane & o;
+            n >>= 1;
+#pragma unroll
+            for (int i = 0; i < K / 2; ++i) {
+                if (i < n) {
+                    const float send = up ? a[i] : a[i + n];
+                    const float keep = up ? a[i + n] : a[i];
+                    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+        } else {
+            a[0] += __shfl_xor_sync(0xffffffffu, a[0], o);
+        }
+    }
+    constexpr int STEP = 32 / K;
+    if ((lane & (STEP - 1)) == 0) dst[lane / STEP] = a[0];
+}
+
 template <int N>
 __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restrict__ dst, int lane) {
-    if constexpr (N >= 8) {
-        float a[4], b[2], c1;
-        const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+    int done = 0;
+    if constexpr (N >= 16) {
+        butterfly_store<16>(v, dst, lane);
+        done = 16;
+    } else if constexpr (N >= 8) {
+        butterfly_store<8>(v, dst, lane);
+        done = 8;
+    }
+    if constexpr (N - (N >= 16 ? 16 : (N >= 8 ? 8 : 0)) >= 3) {
+        constexpr int D0 = N >= 16 ? 16 : (N >= 8 ? 8 : 0);
+        float w[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = up16 ? v[i] : v[i + 4];
-            const float keep = up16 ? v[i + 4] : v[i];
-            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float send = up8 ? a[i] : a[i + 2];
-            const float keep = up8 ? a[i + 2] : a[i];
-            b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
+        for (int i = 0; i < 4; ++i) w[i] = (D0 + i < N) ? v[D0 + i] : 0.f;
+        float tmp[4];
+        // totals of w[i] land in lane 8 i; store only the real ones
         {
-            const float send = up4 ? b[0] : b[1];
-            const float keep = up4 ? b[1] : b[0];
-            c1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            float a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3];
+            const bool up16 = lane & 16, up8 = lane & 8;
+            const float s0 = up16 ? a0 : a2, k0 = up16 ? a2 : a0;
+            const float s1 = up16 ? a1 : a3, k1 = up16 ? a3 : a1;
+            a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+            a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+            const float s2 = up8 ? a0 : a1, k2 = up8 ? a1 : a0;
+            a0 = k2 + __shfl_xor_sync(0xffffffffu, s2, 8);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 4);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+            tmp[0] = a0;
         }
-        c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
-        c1 += __shfl_xor_sync(0xffffffffu, c1, 1);
-        if ((lane & 3) == 0) dst[lane >> 2] = c1;
+        const int vi = lane >> 3;
+        if ((lane & 7) == 0 && D0 + vi < N) dst[D0 + vi] = tmp[0];
+        done = D0 + 4;
+    }
 #pragma unroll
-        for (int i = 8; i < N; ++i) {
-            const float t = warp_sum(v[i]);
-            if (lane == 0) dst[i] = t;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < N; ++i) {
+        if (i >= done) {
             const float t = warp_sum(v[i]);
             if (lane == 0) dst[i] = t;
         }
@@ -375,43 +412,56 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
 // ------------------------------------------------------------------------------------------------
 // Hot-path body: per-warp bulk-async pipelines (see spb_fast.cuh).  grid = (ctas_per_pair, pairs)
 //   part_pair : [cta][NACC]      part_seg : [tile][NSEG]
+//
+// A warp owns GROUPS of SPB_GROUP consecutive tiles (the warps of a CTA take adjacent groups, CTAs stride over the
+// pair).  The per-segment partial sums are reduced across the warp once per run of same-segment tiles inside a
+// group (a tile never straddles segments, a group may) instead of once per tile: the 8-value butterfly and its
+// store are ~70 of the ~150 instructions a lane spends per tile outside the point loop.  The run's sum lands in
+// the slot of its last tile, the other slots of the run receive zeros, so the finalize kernels are unchanged.
+//
+// SPB_TOUCH: the four bilinear taps are the only global loads of a point and the first touch of a target row by
+// an SM pays L2 / HBM latency.  Successive points of a lane (32 points apart in the segment's row-major order)
+// move by a nearly constant texel offset, so after consuming point j the lane touches the cache line it expects
+// point j+1 to need (2 off_j - off_{j-1}, bottom row) with a plain 4-byte load into a register nobody reads: the
+// line is in L1 one point-time (~1.5 k cycles) before the real taps ask for it.  (`prefetch.global.L1` lands the
+// line in L2 only on this part -- measured in round 1, profiles/README.md.)
 // ------------------------------------------------------------------------------------------------
-#ifndef SPB_TRG_PREFETCH
-#define SPB_TRG_PREFETCH 0                      // 1: per-line L2 prefetch of the target image, 2: bulk (TMA) prefetch
+#ifndef SPB_GROUP
+#define SPB_GROUP 4                             // tiles per warp group (power of two)
 #endif
-#ifndef SPB_CTA_CONTIG
-#define SPB_CTA_CONTIG 0                        // 1: contiguous tile run per CTA instead of CTA-strided tiles
-#endif
-#ifndef SPB_PACK_EVICT
-#define SPB_PACK_EVICT 0                        // 1: evict-first L2 hint on the tile-stream copies
-#endif
-#if SPB_CTX_CONST
-// EXPERIMENT (default off, unmeasured; SASS inspected offline: the gradient kernel's loop goes from 145 instructions with 12
-// LDS to 137 with 5 LDS + 5 LDC).  The per-pair context as a module-global constant array: one launch (k_fill_pair_ctx) folds pose / intrinsics / affine
-// of every pair into global scratch, cudaMemcpyToSymbolAsync moves it here (driver-managed coherence of the constant
-// cache), and the fused kernel's context reads become LDC through the constant cache instead of ~10 broadcast LDS per
-// 32 points on the L1 LSU data pipe (74.7 % busy in gradient mode, profiles/README.md).  One symbol per module: launches
-// that use it must be ordered on one stream.
-#define SPB_CTX_MAXPAIRS 256
-__constant__ float c_pair_ctx[SPB_CTX_MAXPAIRS][F_N];
+#ifndef SPB_TOUCH
+#define SPB_TOUCH 1                             // 0: off, 1: touch the predicted bottom-row line, 2: both rows
 #endif
 
-template <int MODE, int NP, bool AFF, bool CTXC = false>
+// asynchronous 4-byte copy global -> a scratch word in shared memory (SASS LDGSTS): allocates the line in L1 like
+// any cached load, has no destination register (a plain load whose result is dead is removed by ptxas) and is never
+// waited for
+__device__ __forceinline__ void touch_line(const float4* p, uint32_t sink) {
+    asm volatile("cp.async.ca.shared.global.L2::256B [%0], [%1], 4;" ::"r"(sink), "l"(p) : "memory");
+}
+
+template <int MODE, int NP, bool AFF>
 __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair& pr, float irls_eps,
                                                 float* __restrict__ part_pair, float* __restrict__ part_seg) {
     constexpr int NACC = Sizes<MODE, NP>::NACC;
     constexpr int NSEG = Sizes<MODE, NP>::NSEG;
+    constexpr int GS = SPB_GROUP;
     extern __shared__ __align__(128) uint32_t s_dyn[];
     __shared__ __align__(16) float s_ctx[F_N];
     __shared__ float s_shift[SPB_NSHIFT];
     __shared__ float s_red[SPB_WARPS * NACC];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#if SPB_TOUCH
+    __shared__ uint32_t s_sink[4];                          // landing word of the touch copies (never read)
+    const uint32_t sink = smem_u32(s_sink);
+#endif
+    const int lane = threadIdx.x & 31;
+    // broadcast from lane 0: tells the compiler the warp index -- and with it the tile / slot / phase bookkeeping of
+    // the loop below -- is warp-uniform, so it can live in uniform registers instead of the 80 vector registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     uint32_t* ring = s_dyn + warp * (SPB_WSTAGES * SPB_SLOT_WORDS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + SPB_WARPS * SPB_WSTAGES * SPB_SLOT_WORDS) + warp * SPB_WSTAGES;
 
-    if constexpr (!CTXC) {
-        if (threadIdx.x < 32) fill_fast_ctx(s_ctx, pr, g.K, g.H, g.W);
-    }
+    if (threadIdx.x < 32) fill_fast_ctx(s_ctx, pr, g.K, g.H, g.W);
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < SPB_WSTAGES; ++s) mbar_init(smem_u32(bars + s), 1);
@@ -420,65 +470,36 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     const int nshift = min(g.n_seg, SPB_NSHIFT);
     for (int b = threadIdx.x; b < nshift; b += blockDim.x) s_shift[b] = __ldg(pr.k + b) - __ldg(g.seg_lkp + b);
     __syncthreads();
-#if SPB_CTX_CONST
-    const float* c = CTXC ? c_pair_ctx[blockIdx.y] : s_ctx;
-#else
     const float* c = s_ctx;
-#endif
 
-#if SPB_CTA_CONTIG
-    // every CTA owns one contiguous run of tiles, its warps march through it side by side
-    const int per = ((g.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x + SPB_WARPS - 1) / SPB_WARPS * SPB_WARPS;
-    const int WS = SPB_WARPS;
-    const int t_first = blockIdx.x * per + warp;
-    const int t_end = min(g.n_tiles, (int)(blockIdx.x + 1) * per);
-#else
-    const int WS = gridDim.x * SPB_WARPS;                  // tile stride of this warp
-    const int t_first = blockIdx.x * SPB_WARPS + warp;
-    const int t_end = g.n_tiles;
-#endif
+    const int n_tiles = g.n_tiles;
+    const int WS = gridDim.x * SPB_WARPS * GS;             // tile stride between two groups of this warp
+    const int t_first = (blockIdx.x * SPB_WARPS + warp) * GS;
     const uint32_t* pack = pr.tile_pack;
+    // successor of tile t in this warp's sequence (>= n_tiles: none)
+    auto next_tile = [&](int t) {
+        const int tn = t + 1;
+        return ((tn & (GS - 1)) != 0 && tn < n_tiles) ? tn : (tn - 1) - ((tn - 1) & (GS - 1)) + WS;
+    };
 
     // producer (lane 0): ONE bulk copy brings the whole tile block (header + uv + logd + r + g + b)
-#if SPB_PACK_EVICT
-    const uint64_t pol = l2_policy_evict_first();
-#endif
     auto issue = [&](int t, int slot) {
         const uint32_t bar = smem_u32(bars + slot);
         mbar_expect_tx(bar, SPB_PACK_WORDS * 4u);
-#if SPB_PACK_EVICT
-        bulk_g2s_hint(smem_u32(ring + slot * SPB_SLOT_WORDS), pack + (size_t)t * SPB_PACK_WORDS, SPB_PACK_WORDS * 4u, bar,
-                      pol);
-#else
         bulk_g2s(smem_u32(ring + slot * SPB_SLOT_WORDS), pack + (size_t)t * SPB_PACK_WORDS, SPB_PACK_WORDS * 4u, bar);
-#endif
     };
-#if SPB_TRG_PREFETCH == 1
-    {   // pull the pair's target image towards L2 while the first tiles are in flight: the gathers of the
-        // tile loop then pay L2 latency instead of DRAM latency (the CTAs of a pair share the work)
-        const char* tb = reinterpret_cast<const char*>(pr.trg_rgba);
-        const int nlines = (pr.Hl * pr.Wl * 16 + 127) >> 7;
-        for (int l = blockIdx.x * SPB_THREADS + threadIdx.x; l < nlines; l += gridDim.x * SPB_THREADS)
-            prefetch_l2_line(tb + ((size_t)l << 7));
-    }
-#elif SPB_TRG_PREFETCH == 2
     if (lane == 0) {
-        const char* tb = reinterpret_cast<const char*>(pr.trg_rgba);
-        const int nchunks = (pr.Hl * pr.Wl * 16) >> 12;          // 4 KB chunks (tail left to demand loads)
-        for (int l = blockIdx.x * SPB_WARPS + warp; l < nchunks; l += gridDim.x * SPB_WARPS)
-            prefetch_l2_bulk(tb + ((size_t)l << 12), 4096u);
-    }
-#endif
-    if (lane == 0) {
+        int t = t_first;
 #pragma unroll
         for (int s = 0; s < SPB_WSTAGES - 1; ++s) {
-            const int t = t_first + s * WS;
-            if (t < t_end) issue(t, s);
+            if (t < n_tiles) issue(t, s);
+            t = next_tile(t);
         }
     }
 
     const float4* trg = reinterpret_cast<const float4*>(pr.trg_rgba);
     const int Wl = pr.Wl;
+    [[maybe_unused]] const uint32_t last_texel = (uint32_t)(pr.Hl * Wl - 1);
     constexpr bool PACKED = (MODE == MODE_GN && NP == 6);   // FFMA2 formulation (spb_gn_packed.cuh)
     float acc[NACC];
 #pragma unroll
@@ -487,27 +508,31 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     pacc.zero();
     GradAcc gacc;
     gacc.zero();
+    float seg[NSEG];
+#pragma unroll
+    for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
+    GnSeg6 pseg;
+    pseg.zero();
 
     int slot = 0, fill = SPB_WSTAGES - 1;                  // slot consumed now / slot refilled now
     uint32_t phase = 0;
-    for (int t = t_first; t < t_end; t += WS) {
-        if (lane == 0) {
-            const int tn = t + (SPB_WSTAGES - 1) * WS;
-            if (tn < t_end) issue(tn, fill);
-        }
-        mbar_wait(smem_u32(bars + slot), phase);
+    int t_ahead = t_first;                                 // tile the producer issues next
+#pragma unroll
+    for (int s = 0; s < SPB_WSTAGES - 1; ++s) t_ahead = next_tile(t_ahead);
+#if SPB_TOUCH
+    int off_prev = -1;                                     // texel offset of this lane's previous valid point in the run
+#endif
+    int t = t_first;
+    if (t < n_tiles) mbar_wait(smem_u32(bars + slot), phase);
+    while (t < n_tiles) {
+        if (lane == 0 && t_ahead < n_tiles) issue(t_ahead, fill);
+        t_ahead = next_tile(t_ahead);
         const uint32_t* sl = ring + slot * SPB_SLOT_WORDS;
-        const int sidx = (int)sl[0], cnt = (int)sl[1];
+        const int sidx = (int)sl[0];
         const float shift = (sidx < SPB_NSHIFT) ? s_shift[sidx] : (__ldg(pr.k + sidx) - __ldg(g.seg_lkp + sidx));
         const uint32_t* s_uv = sl + 4;
         const float* s_f = reinterpret_cast<const float*>(sl + 4);
-        float seg[NSEG];
-#pragma unroll
-        for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
-        GnSeg6 pseg;
-        pseg.zero();
         // padding entries of a partial tile are zero words: uv bit 31 clear => invalid, no bounds test needed
-        (void)cnt;
         SPB_PRAGMA_UNROLL(SPB_UNROLL)
         for (int j = 0; j < SPB_PPT; ++j) {
             const int i = j * 32 + lane;
@@ -517,6 +542,19 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
             if (ok) {
                 Taps4 tp;
                 load_taps(trg, Wl, q.off, tp);
+#if SPB_TOUCH
+                {
+                    // where this lane's next point (32 points on) is expected: linear extrapolation of the texel offset,
+                    // bottom row.  Out-of-image predictions (and the first point of a run, off_prev = -1) clamp to the
+                    // last texel: a harmless touch.
+                    const uint32_t pred = min((uint32_t)(2 * q.off - off_prev + Wl), last_texel);
+                    touch_line(trg + pred, sink);
+#if SPB_TOUCH == 2
+                    touch_line(trg + (pred >= (uint32_t)Wl ? pred - Wl : 0u), sink);
+#endif
+                }
+                off_prev = q.off;
+#endif
                 const float i0 = s_f[2 * SPB_TILE + i], i1 = s_f[3 * SPB_TILE + i], i2 = s_f[4 * SPB_TILE + i];
                 if constexpr (MODE == MODE_GRAD)
                     point_grad_packed<AFF>(c, tp, q, i0, i1, i2, gacc, seg[0]);
@@ -526,11 +564,37 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
                     point_gn<NP, NACC, NSEG>(c, tp, q, i0, i1, i2, irls_eps, acc, seg);
             }
         }
-        if constexpr (PACKED) pseg.store(seg);
-        tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
         __syncwarp();                                      // every lane is done with this slot
+        // this warp's next tile, its ring slot, and whether it continues the same-segment run (its header says)
+        const int tn = t + 1;
+        const bool group_end = ((tn & (GS - 1)) == 0) || tn >= n_tiles;
+        const int t_next = group_end ? (t - (t & (GS - 1))) + WS : tn;
         fill = slot;
         if (++slot == SPB_WSTAGES) { slot = 0; phase ^= 1u; }
+        bool flush = group_end;
+        if (t_next < n_tiles) {
+            mbar_wait(smem_u32(bars + slot), phase);
+            if constexpr (GS > 1) {
+                if (!group_end) flush = (int)ring[slot * SPB_SLOT_WORDS] != sidx;
+            }
+        }
+        if (flush) {
+            if constexpr (PACKED) {
+                pseg.store(seg);
+                pseg.zero();
+            }
+            tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
+            if constexpr (!PACKED) {
+#pragma unroll
+                for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
+            }
+#if SPB_TOUCH
+            off_prev = -1;
+#endif
+        } else if constexpr (GS > 1) {
+            if (lane < NSEG) part_seg[(size_t)t * NSEG + lane] = 0.f;
+        }
+        t = t_next;
     }
     if constexpr (PACKED) pacc.store(acc);
     if constexpr (MODE == MODE_GRAD) gacc.store(acc);
@@ -595,42 +659,16 @@ k_align_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pa
     align_body_warp<MODE, NP, AFF>(s_g, s_pr, irls_eps, base, base + (size_t)gridDim.x * NACC);
 }
 
-#if SPB_CTX_CONST
-__global__ void k_fill_pair_ctx(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs, int n_pairs,
-                                float* __restrict__ out) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
-    const SpbPair pr = pairs[p];
-    const SpbGeom& g = geoms[pr.geom];
-    float* s = out + (size_t)p * F_N;
-    for (int i = 0; i < F_N; ++i) s[i] = 0.f;
-    fill_fast_ctx_serial(s, pr, g.K, g.H, g.W);
-}
-
-template <int MODE, int NP, bool AFF>
-__global__ void __launch_bounds__(SPB_THREADS, Occ<MODE, NP>::CTAS)
-k_align_global_cc(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs, float irls_eps,
-                  float* __restrict__ work, int64_t work_stride) {
-    constexpr int NACC = Sizes<MODE, NP>::NACC;
-    const int pair = blockIdx.y;
-    __shared__ SpbPair s_pr;
-    __shared__ SpbGeom s_g;
-    if (threadIdx.x == 0) {
-        s_pr = pairs[pair];
-        s_g = geoms[s_pr.geom];
-    }
-    __syncthreads();
-    float* base = work + pair * work_stride;
-    align_body_warp<MODE, NP, AFF, true>(s_g, s_pr, irls_eps, base, base + (size_t)gridDim.x * NACC);
-}
-#endif
-
 // Fixed-order sum over the per-CTA partials [ctas][NACC] (contiguous): the block's threads form R = blockDim / NACC
 // row groups; thread (r, c) adds rows r, r + R, ... of column c (consecutive threads read consecutive floats, 8 loads
 // in flight), the groups meet in shared memory and thread c < NACC adds them in group order.  Returns the total to
 // threads < NACC (0 elsewhere).  A serial loop over several hundred CTAs costs tens of microseconds when one
 // problem owns the whole GPU.  Needs blockDim >= NACC; contains two __syncthreads().
 #define SPB_FIN_SMEM 1024
+#ifndef SPB_FIN_THREADS
+#define SPB_FIN_THREADS 512                     // threads of k_gn_finalize_solve
+#endif
+#define SPB_FIN_THREADS_MAX 512                 // most threads any GN finalize launch uses
 template <int NACC>
 __device__ __forceinline__ float sum_cta_partials(const float* pp, int ctas, float* s_part /* [SPB_FIN_SMEM] */) {
     const int R = min((int)blockDim.x, SPB_FIN_SMEM) / NACC;
@@ -769,7 +807,6 @@ __device__ __forceinline__ void finalize_gn_body(const SpbGeom* __restrict__ geo
                                                  float* __restrict__ out_pair, float* __restrict__ out_seg) {
     constexpr int NACC = Sizes<MODE_GN, NP>::NACC;
     constexpr int NSEG = Sizes<MODE_GN, NP>::NSEG;
-    constexpr int NA = NP * (NP + 1) / 2;
     const int pair = blockIdx.x;
     const SpbGeom& g = geoms[pairs[pair].geom];
     const float* pp = work + pair * work_stride;
@@ -777,60 +814,85 @@ __device__ __forceinline__ void finalize_gn_body(const SpbGeom* __restrict__ geo
     float* op = out_pair + (size_t)pair * SPB_GN_PAIR_NOUT;
     __shared__ float s_part[SPB_FIN_SMEM];
     const float tot = sum_cta_partials<NACC>(pp, ctas, s_part);
-    if (threadIdx.x < NACC) {
-        const float v = tot;
-        // scatter into the fixed 8-column layout
-        const int i = threadIdx.x;
-        if (NP == 8) {
-            op[i] = v;
-        } else {
-            if (i < NA) {            // (r,c) in the 6x6 triangle -> index in the 8x8 triangle
-                int r = 0, rem = i;
-                while (rem >= 6 - r) { rem -= 6 - r; ++r; }
-                const int cc = r + rem;
-                const int idx8 = r * 8 - r * (r - 1) / 2 + (cc - r);
-                op[idx8] = v;
-            } else if (i < NA + 6) {
-                op[SPB_GN_NA + (i - NA)] = v;
-            } else {
-                op[SPB_GN_NA + 8 + (i - NA - 6)] = v;
-            }
-        }
-    }
-    if (NP == 6 && threadIdx.x < SPB_GN_PAIR_NOUT) {
-        // zero the affine rows/cols + pad that the 6-column accumulation does not touch
-        const int i = threadIdx.x;
-        bool touched = false;
-        if (i < SPB_GN_NA) {
-            int r = 0, rem = i;
-            while (rem >= 8 - r) { rem -= 8 - r; ++r; }
-            const int cc = r + rem;
-            touched = (r < 6 && cc < 6);
-        } else if (i < SPB_GN_NA + 8) {
-            touched = (i - SPB_GN_NA) < 6;
-        } else {
-            touched = (i - SPB_GN_NA - 8) < 3;
-        }
-        if (!touched) op[i] = 0.f;
-    }
-    if (NP == 8 && threadIdx.x == SPB_GN_PAIR_NOUT - 1) op[threadIdx.x] = 0.f;
     const int so = seg_off[pair];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    // two segments per warp per round; lane i < NSEG ends up with value i of the segment (seg_sum2)
-    for (int b = warp; b < g.n_seg; b += 2 * nwarps) {
-        const int b2 = b + nwarps;
-        const bool two = b2 < g.n_seg;
-        float v, v2;
-        seg_sum2<NSEG>(ps, g.seg_tile[b], g.seg_tile[b + 1], two ? g.seg_tile[b2] : 0, two ? g.seg_tile[b2 + 1] : 0,
-                       lane, v, v2);
-        // fixed 10-float record: B[0..7], D, g_d (the 6-column accumulation leaves B[6], B[7] zero)
-        const int slot = (NP == 8) ? lane : (lane < 6 ? lane : lane + 2);
-        if (lane < NSEG) {
-            out_seg[(size_t)(so + b) * SPB_GN_SEG_NOUT + slot] = v;
-            if (two) out_seg[(size_t)(so + b2) * SPB_GN_SEG_NOUT + slot] = v2;
-        } else if (NP == 6 && lane < 10) {                   // lanes 8, 9 -> slots 6, 7
-            out_seg[(size_t)(so + b) * SPB_GN_SEG_NOUT + lane - 2] = 0.f;
-            if (two) out_seg[(size_t)(so + b2) * SPB_GN_SEG_NOUT + lane - 2] = 0.f;
+    if constexpr (NP == 8) {
+        if (threadIdx.x < NACC) op[threadIdx.x] = tot;
+        if (threadIdx.x == SPB_GN_PAIR_NOUT - 1) op[threadIdx.x] = 0.f;
+        // two segments per warp per round; lane i < NSEG ends up with value i of the segment (seg_sum2)
+        for (int b = warp; b < g.n_seg; b += 2 * nwarps) {
+            const int b2 = b + nwarps;
+            const bool two = b2 < g.n_seg;
+            float v, v2;
+            seg_sum2<NSEG>(ps, g.seg_tile[b], g.seg_tile[b + 1], two ? g.seg_tile[b2] : 0, two ? g.seg_tile[b2 + 1] : 0,
+                           lane, v, v2);
+            if (lane < NSEG) {       // fixed 10-float record: B[0..7], D, g_d
+                out_seg[(size_t)(so + b) * SPB_GN_SEG_NOUT + lane] = v;
+                if (two) out_seg[(size_t)(so + b2) * SPB_GN_SEG_NOUT + lane] = v2;
+            }
+        }
+    } else {
+        // 6 pose columns (spb_gn_packed.cuh): the per-run records hold rows 0..2 of the pose block and g_0..g_3; the
+        // depth column of a segment is -(t_x J_0 + t_y J_1 + t_z J_2), so B_b, D_b, g_d,b are combinations of the
+        // segment's sums (gn6_segment_record) and rows 0..2 of the pose block are the sums over all segments.
+        __shared__ float s_rows[SPB_FIN_THREADS_MAX / 32][SPB_GN6_NRUN];
+        const float* pose = pairs[pair].pose;
+        const double t[3] = {(double)pose[3], (double)pose[7], (double)pose[11]};
+        float rows = 0.f;                                       // lane l < 19: running sum of value l over this warp's segments
+        for (int b = warp; b < g.n_seg; b += 2 * nwarps) {
+            const int b2 = b + nwarps;
+            const bool two = b2 < g.n_seg;
+            float v, v2;
+            seg_sum2<NSEG>(ps, g.seg_tile[b], g.seg_tile[b + 1], two ? g.seg_tile[b2] : 0, two ? g.seg_tile[b2 + 1] : 0,
+                           lane, v, v2);
+            if (lane >= NSEG) { v = 0.f; v2 = 0.f; }
+            if (!two) v2 = 0.f;
+            rows += v;
+            rows += v2;
+            // lane i < 6 derives B[i], lane 6 D, lane 7 g_d; lanes 8, 9 write the zero affine slots of the record
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                const float val = which ? v2 : v;
+                const int bb = which ? b2 : b;
+                const int col = lane < 6 ? lane : 0;
+                double r0 = (double)__shfl_sync(0xffffffffu, val, lane < 6 ? gn6_run_index(0, col) : (lane == 7 ? 15 : 0));
+                double r1 = (double)__shfl_sync(0xffffffffu, val, lane < 6 ? gn6_run_index(1, col) : (lane == 7 ? 16 : 1));
+                double r2 = (double)__shfl_sync(0xffffffffu, val, lane < 6 ? gn6_run_index(2, col) : (lane == 7 ? 17 : 2));
+                double rec = -(t[0] * r0 + t[1] * r1 + t[2] * r2);       // B[lane] (lanes 0..5), g_d (lane 7)
+                // D = -(t . B[0..2]) = t^T A[0:3,0:3] t
+                const double b0 = __shfl_sync(0xffffffffu, rec, 0), b1 = __shfl_sync(0xffffffffu, rec, 1),
+                             b2v = __shfl_sync(0xffffffffu, rec, 2);
+                if (lane == 6) rec = -(t[0] * b0 + t[1] * b1 + t[2] * b2v);
+                if ((which == 0 || two) && lane < 10) {
+                    const int slot = lane < 6 ? lane : (lane < 8 ? lane + 2 : lane - 2);   // B[6], B[7] (affine) stay zero
+                    out_seg[(size_t)(so + bb) * SPB_GN_SEG_NOUT + slot] = lane < 8 ? (float)rec : 0.f;
+                }
+            }
+        }
+        if (lane < SPB_GN6_NRUN) s_rows[warp][lane] = rows;
+        __syncthreads();
+        if (threadIdx.x < SPB_GN_PAIR_NOUT) op[threadIdx.x] = 0.f;   // affine rows / columns and padding stay zero
+        __syncthreads();
+        if (threadIdx.x < SPB_GN6_NRUN) {
+            float v = 0.f;
+            for (int w = 0; w < nwarps; ++w) v += s_rows[w][threadIdx.x];
+            const int i = threadIdx.x;
+            if (i < 6) op[tri8(0, i)] = v;
+            else if (i < 11) op[tri8(1, i - 5)] = v;
+            else if (i < 15) op[tri8(2, i - 9)] = v;
+            else op[SPB_GN_NA + (i - 15)] = v;                   // g_0..g_3
+        }
+        // rotation block, g_4, g_5, cost from the per-CTA partials (threads < NACC hold `tot`)
+        if (threadIdx.x < 9) {
+            const int i = threadIdx.x;
+            int idx;
+            if (i == 0) idx = tri8(3, 3);
+            else if (i < 3) idx = tri8(3, 3 + i);
+            else if (i < 5) idx = tri8(4, 4 + (i - 3));
+            else if (i == 5) idx = tri8(5, 5);
+            else if (i < 8) idx = SPB_GN_NA + 4 + (i - 6);
+            else idx = SPB_GN_NA + 8;                            // cost
+            op[idx] = tot;
         }
     }
 }
@@ -843,9 +905,6 @@ __global__ void k_finalize_gn(const SpbGeom* __restrict__ geoms, const SpbPair* 
 }
 
 // finalize + damped solve + retraction in ONE launch (one CTA per problem): the second kernel of a GN iteration
-#ifndef SPB_FIN_THREADS
-#define SPB_FIN_THREADS 512
-#endif
 template <int NP>
 __global__ void __launch_bounds__(SPB_FIN_THREADS)
 k_gn_finalize_solve(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pairs,
@@ -908,12 +967,27 @@ __global__ void k_finalize_points(int ctas, int P, const float* __restrict__ wor
 // ------------------------------------------------------------------------------------------------
 // host-side launch helpers (C ABI)
 // ------------------------------------------------------------------------------------------------
+static int sm_count() {
+    // queried once (per process; every rank sees one kind of GPU)
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+            n = v;
+        else
+            return 148;
+    }
+    return n;
+}
+
 static inline int ctas_for(int n_tiles, int n_pairs, int occ) {
-    // every warp streams a strided set of tiles through its own ring.  Size the grid to a whole number of waves
-    // of the kernel's occupancy (`occ` CTAs/SM on 148 SMs): ~4 waves over all pairs, rounded DOWN so the last
-    // wave is nearly full (a 5.3-wave grid wastes a third of its last wave).
-    const int max_ctas = (n_tiles + SPB_WARPS - 1) / SPB_WARPS;
-    const int slots = 148 * occ;
+    // every warp streams a strided set of tile groups through its own ring.  Size the grid to a whole number of waves
+    // of the kernel's occupancy (`occ` CTAs/SM): ~4 waves over all pairs, rounded DOWN so the last wave is nearly
+    // full (a 5.3-wave grid wastes a third of its last wave).
+    const int n_groups = (n_tiles + SPB_GROUP - 1) / SPB_GROUP;
+    const int max_ctas = (n_groups + SPB_WARPS - 1) / SPB_WARPS;
+    const int slots = sm_count() * occ;
     if (n_pairs < 1) n_pairs = 1;
     if ((long long)n_pairs * max_ctas <= slots) return max_ctas;
     int want = (slots * 4) / n_pairs;
@@ -937,16 +1011,21 @@ static inline cudaError_t allow_dyn_smem(K kernel) {
 
 static inline int ctas_for_points(int P) {
     int want = (P + SPB_THREADS * 4 - 1) / (SPB_THREADS * 4);
-    if (want > 148 * 4) want = 148 * 4;
+    if (want > sm_count() * 4) want = sm_count() * 4;
     if (want < 1) want = 1;
     return want;
 }
 
 extern "C" int64_t spb_workspace_floats(const SpbGeom* geom, int B, int gn) {
     const int ctas = ctas_max(geom->n_tiles, B);
-    const int nacc = gn ? Sizes<MODE_GN, 8>::NACC : SPB_PAIR_NOUT;
-    const int nseg = gn ? Sizes<MODE_GN, 8>::NSEG : 1;
+    const int nacc = gn ? SPB_MAX_NACC : SPB_PAIR_NOUT;
+    const int nseg = gn ? SPB_MAX_NSEG : 1;
     return (int64_t)B * ((int64_t)ctas * nacc + (int64_t)geom->n_tiles * nseg);
+}
+
+// floats per pair of the batched entry points' workspace (any mode): per-CTA accumulators + per-tile run records
+extern "C" int64_t spb_gn_work_stride(int max_tiles, int n_pairs) {
+    return (int64_t)ctas_max(max_tiles, n_pairs) * SPB_MAX_NACC + (int64_t)max_tiles * SPB_MAX_NSEG;
 }
 
 extern "C" int64_t spb_workspace_floats_points(int P) { return (int64_t)ctas_for_points(P) * SPB_PAIR_NOUT; }
@@ -1137,25 +1216,6 @@ k_grad_finalize_adam(const SpbGeom* __restrict__ geoms, const SpbPair* __restric
 static int launch_grad_align(const SpbGeom* geoms, const SpbPair* pairs, int n_pairs, int ctas, int with_affine,
                              float* work, int64_t work_stride, cudaStream_t st) {
     dim3 grid(ctas, n_pairs);
-#if SPB_CTX_CONST
-    if (n_pairs <= SPB_CTX_MAXPAIRS && (int64_t)n_pairs * work_stride >= (int64_t)n_pairs * F_N) {
-        // context of every pair -> scratch at the front of `work` (overwritten by the partials afterwards) -> constant array
-        k_fill_pair_ctx<<<(n_pairs + 63) / 64, 64, 0, st>>>(geoms, pairs, n_pairs, work);
-        SPB_CHECK_LAUNCH();
-        cudaError_t e = cudaMemcpyToSymbolAsync(c_pair_ctx, work, (size_t)n_pairs * F_N * sizeof(float), 0,
-                                                cudaMemcpyDeviceToDevice, st);
-        if (e != cudaSuccess) return (int)e;
-        if (with_affine) {
-            if ((e = allow_dyn_smem(k_align_global_cc<MODE_GRAD, 6, true>)) != cudaSuccess) return (int)e;
-            k_align_global_cc<MODE_GRAD, 6, true><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
-        } else {
-            if ((e = allow_dyn_smem(k_align_global_cc<MODE_GRAD, 6, false>)) != cudaSuccess) return (int)e;
-            k_align_global_cc<MODE_GRAD, 6, false><<<grid, SPB_THREADS, SPB_FAST_DYN_SMEM, st>>>(geoms, pairs, 0.f, work, work_stride);
-        }
-        SPB_CHECK_LAUNCH();
-        return SPB_OK;
-    }
-#endif
     if (with_affine) {
         cudaError_t e = allow_dyn_smem(k_align_global<MODE_GRAD, 6, true>);
         if (e != cudaSuccess) return (int)e;

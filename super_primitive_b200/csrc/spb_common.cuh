@@ -9,11 +9,10 @@
 #ifndef SPB_INGEST_FUSED
 #define SPB_INGEST_FUSED 0                      // 1: fused source ingest (spb_ingest.cu)
 #endif
-#ifndef SPB_CTX_CONST
-#define SPB_CTX_CONST 0                         // 1: gradient mode of the batched solver reads the per-pair context from a
-#endif                                          //    __constant__ array (spb_align.cu)
 
-#define SPB_WARPS 8
+#ifndef SPB_WARPS
+#define SPB_WARPS 8                             // warps per CTA of the fused kernels (tunable)
+#endif
 #define SPB_THREADS (SPB_WARPS * 32)
 #define SPB_PPT (SPB_TILE / 32)   // points per lane per tile
 

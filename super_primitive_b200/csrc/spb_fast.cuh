@@ -53,25 +53,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-// same copy with an L2 eviction-priority hint (the tile stream is read exactly once per launch)
-__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
-                                              uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void prefetch_l2_line(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
@@ -122,34 +103,6 @@ __device__ __forceinline__ void fill_fast_ctx(float* s, const SpbPair& pr, const
     }
 }
 
-#if SPB_CTX_CONST
-// one thread writes the whole context (constant-context experiment, spb_align.cu): fill_fast_ctx's two halves in turn
-__device__ __forceinline__ void fill_fast_ctx_serial(float* s, const SpbPair& pr, const float* Ksrc, int H, int W) {
-    const float ifx = 1.0f / Ksrc[0], ify = 1.0f / Ksrc[4];
-    for (int i = 0; i < 3; ++i) {
-        s[F_MAT(i, 0)] = pr.pose[4 * i] * ifx;
-        s[F_MAT(i, 1)] = pr.pose[4 * i + 1] * ify;
-        s[F_MAT(i, 2)] = pr.pose[4 * i + 2];
-        s[F_TR(i)] = pr.pose[4 * i + 3];
-    }
-    s[F_CX] = Ksrc[2];
-    s[F_CY] = Ksrc[5];
-    const float tiw = 2.0f * (1.0f / (float)(W - 1)), tih = 2.0f * (1.0f / (float)(H - 1));
-    const float sx = 0.5f * (float)(pr.Wl - 1), sy = 0.5f * (float)(pr.Hl - 1);
-    const float fxt = pr.K_trg[0], fyt = pr.K_trg[4], cxt = pr.K_trg[2], cyt = pr.K_trg[5];
-    float a = 0.f, b = 0.f;
-    if (pr.aff_src != nullptr && pr.aff_trg != nullptr) {
-        a = pr.aff_trg[0] - pr.aff_src[0];
-        b = pr.aff_trg[1] - pr.aff_src[1];
-    }
-    const float ea = expf(-a);
-    s[F_AX] = fxt * tiw; s[F_BX] = fmaf(cxt, tiw, -1.0f);
-    s[F_AY] = fyt * tih; s[F_BY] = fmaf(cyt, tih, -1.0f);
-    s[F_SX] = sx; s[F_SY] = sy; s[F_TAU] = pr.tau; s[F_EA] = ea; s[F_BB] = b;
-    const float cu = -ea * (sx * tiw) * fxt, cv = -ea * (sy * tih) * fyt;
-    s[F_CU] = cu; s[F_CV] = cv; s[F_CUU] = cu * cu; s[F_CUV] = cu * cv; s[F_CUV2] = cu * cv; s[F_CVV] = cv * cv;
-}
-#endif
 
 // geometry shared by both modes: returns validity, fills the projected quantities
 struct Proj {
@@ -205,13 +158,7 @@ __device__ __forceinline__ float4 ldg_l2_256(const float4* p) {
 struct Taps4 {
     float4 nw, ne, sw, se;
 };
-#ifndef SPB_DIAG_TAPS_HOT
-#define SPB_DIAG_TAPS_HOT 0                     // DIAGNOSTIC ONLY (wrong results): every gather hits the same few L1 lines,
-#endif                                          // the kernel time that remains is the floor latency hiding could reach
 __device__ __forceinline__ void load_taps(const float4* __restrict__ trg, int Wl, int off, Taps4& t) {
-#if SPB_DIAG_TAPS_HOT
-    off &= 31;
-#endif
     const float4* p0 = trg + off;
 #if SPB_TAP_L2_256
     t.nw = ldg_l2_256(p0); t.ne = ldg_l2_256(p0 + 1); t.sw = ldg_l2_256(p0 + Wl); t.se = ldg_l2_256(p0 + Wl + 1);

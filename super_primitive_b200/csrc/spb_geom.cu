@@ -511,4 +511,4 @@ extern "C" int spb_depth_splat_points(const float* pts, int P, const float* K, i
 
 extern "C" int spb_tile_points(void) { return SPB_TILE; }
 
-extern "C" int spb_version(void) { return 105 + 1000 * (SPB_INGEST_FUSED + 2 * SPB_CTX_CONST); }
+extern "C" int spb_version(void) { return 106 + 1000 * SPB_INGEST_FUSED; }

@@ -8,44 +8,64 @@
 #pragma once
 #include "spb_fast.cuh"
 
-struct GnAcc6 {            // upper triangle of the 6x6 pose block, g_p, cost terms (canonical order in store())
-    float2 a00, a02, a04;  // (0,0)(0,1) (0,2)(0,3) (0,4)(0,5)
-    float a11;
-    float2 a12, a14;       // (1,2)(1,3) (1,4)(1,5)
-    float2 a22, a24;       // (2,2)(2,3) (2,4)(2,5)
+// Depth-column identity (exact for a live reciprocal): a depth change moves a point along its epipolar line, so the
+// Jacobian column of the segment's log-depth seed is a fixed combination of the first three twist columns,
+//     j_d = -(t_x J_0 + t_y J_1 + t_z J_2).
+// The kernel therefore never forms j_d: it accumulates rows 0..2 of J^T W J and g_0..g_3 PER RUN of same-segment tiles
+// (19 values, summed over the segment's points by the finalize kernel, which derives B_b, D_b, g_d,b from them --
+// gn6_segment_record below -- and the pose block's rows 0..2 as the sum over the segments), and only the 3x3 rotation
+// block, g_4, g_5 and the cost per warp.  28 live accumulators instead of 36 and 24 instead of 33 update instructions.
+#define SPB_GN6_NRUN 19        // per-run values: A[0][0..5], A[1][1..5], A[2][2..5], g_0..g_3
+#define SPB_GN6_NACC 12        // per-warp values: A[3][3..5], A[4][4..5], A[5][5], g_4, g_5, cost, 0, 0, 0
+
+struct GnAcc6 {            // rotation block of the pose matrix (upper triangle), g_4, g_5, cost
     float a33;
     float2 a34;            // (3,4)(3,5)
     float2 a44;            // (4,4)(4,5)
     float a55;
-    float2 g01, g23, g45;
+    float2 g45;
     float cost;            // sum |r| ; the weighted cost and the valid count are not accumulated on this path
     __device__ __forceinline__ void zero() {
-        const float2 z = make_float2(0.f, 0.f);
-        a00 = a02 = a04 = a12 = a14 = a22 = a24 = a34 = a44 = g01 = g23 = g45 = z;
-        a11 = a33 = a55 = cost = 0.f;
+        a34 = a44 = g45 = make_float2(0.f, 0.f);
+        a33 = a55 = cost = 0.f;
     }
-    __device__ __forceinline__ void store(float (&o)[30]) const {
-        o[0] = a00.x; o[1] = a00.y; o[2] = a02.x; o[3] = a02.y; o[4] = a04.x; o[5] = a04.y;
-        o[6] = a11; o[7] = a12.x; o[8] = a12.y; o[9] = a14.x; o[10] = a14.y;
-        o[11] = a22.x; o[12] = a22.y; o[13] = a24.x; o[14] = a24.y;
-        o[15] = a33; o[16] = a34.x; o[17] = a34.y;
-        o[18] = a44.x; o[19] = a44.y; o[20] = a55;
-        o[21] = g01.x; o[22] = g01.y; o[23] = g23.x; o[24] = g23.y; o[25] = g45.x; o[26] = g45.y;
-        o[27] = cost; o[28] = 0.f; o[29] = 0.f;
+    __device__ __forceinline__ void store(float (&o)[SPB_GN6_NACC]) const {
+        o[0] = a33; o[1] = a34.x; o[2] = a34.y; o[3] = a44.x; o[4] = a44.y; o[5] = a55;
+        o[6] = g45.x; o[7] = g45.y; o[8] = cost; o[9] = 0.f; o[10] = 0.f; o[11] = 0.f;
     }
 };
 
-struct GnSeg6 {            // depth column of the tile's segment: B[0..5], D, g_d
-    float2 b01, b23, b45;
-    float d, gd;
+struct GnSeg6 {            // rows 0..2 of the pose block + g_0..g_3 over the points of one same-segment run
+    float2 a00, a02, a04;  // (0,0)(0,1) (0,2)(0,3) (0,4)(0,5)
+    float a11;
+    float2 a12, a14;       // (1,2)(1,3) (1,4)(1,5)
+    float2 a22, a24;       // (2,2)(2,3) (2,4)(2,5)
+    float2 g01, g23;
     __device__ __forceinline__ void zero() {
-        b01 = b23 = b45 = make_float2(0.f, 0.f);
-        d = gd = 0.f;
+        a00 = a02 = a04 = a12 = a14 = a22 = a24 = g01 = g23 = make_float2(0.f, 0.f);
+        a11 = 0.f;
     }
-    __device__ __forceinline__ void store(float (&o)[8]) const {
-        o[0] = b01.x; o[1] = b01.y; o[2] = b23.x; o[3] = b23.y; o[4] = b45.x; o[5] = b45.y; o[6] = d; o[7] = gd;
+    __device__ __forceinline__ void store(float (&o)[SPB_GN6_NRUN]) const {
+        o[0] = a00.x; o[1] = a00.y; o[2] = a02.x; o[3] = a02.y; o[4] = a04.x; o[5] = a04.y;
+        o[6] = a11; o[7] = a12.x; o[8] = a12.y; o[9] = a14.x; o[10] = a14.y;
+        o[11] = a22.x; o[12] = a22.y; o[13] = a24.x; o[14] = a24.y;
+        o[15] = g01.x; o[16] = g01.y; o[17] = g23.x; o[18] = g23.y;
     }
 };
+
+// entry (r, i), r < 3, of the symmetric pose block inside a per-run record S[19]
+__host__ __device__ inline int gn6_run_index(int r, int i) {
+    if (i < r) { const int t = r; r = i; i = t; }
+    return r == 0 ? i : (r == 1 ? 5 + i : 9 + i);
+}
+// B_b[0..5], D_b, g_d,b of one segment from the sums S[19] over its points and the translation t of the pose
+// (float64: D is a quadratic form with cancellation between its terms)
+__host__ __device__ inline void gn6_segment_record(const double* S, const double* t, double* out /* [8] */) {
+    for (int i = 0; i < 6; ++i)
+        out[i] = -(t[0] * S[gn6_run_index(0, i)] + t[1] * S[gn6_run_index(1, i)] + t[2] * S[gn6_run_index(2, i)]);
+    out[6] = -(t[0] * out[0] + t[1] * out[1] + t[2] * out[2]);
+    out[7] = -(t[0] * S[15] + t[1] * S[16] + t[2] * S[17]);
+}
 
 // scalar * pair (+ pair): the scalar is a broadcast operand, no extra instruction
 __device__ __forceinline__ float2 fma2(float s, float2 b, float2 c) { return __ffma2_rn(make_float2(s, s), b, c); }
@@ -96,46 +116,37 @@ __device__ __forceinline__ void point_gn6_packed(const float* __restrict__ c, co
     H = __fmul2_rn(H, *reinterpret_cast<const float2*>(c + F_CU));        // (cu, cv)
     const float Guu = GA.x, Guv = GA.y, Gvv = GB.y, hu = H.x, hv = H.y;
 
-    // mu = d x_/d(xi,k), mv = d y_/d(xi,k) with mu0 = rho, mu1 = 0, mv0 = 0, mv1 = rho
+    // mu = d x_/d xi, mv = d y_/d xi with mu0 = rho, mu1 = 0, mv0 = 0, mv1 = rho
     const float rho = q.rho, xb = q.xb, yb = q.yb;
     const float xy = xb * yb;
     const float2 mu23 = make_float2(-rho * xb, -xy);
     const float2 mu45 = make_float2(fmaf(xb, xb, 1.0f), -yb);
     const float2 mv23 = make_float2(-rho * yb, -fmaf(yb, yb, 1.0f));
     const float2 mv45 = make_float2(xy, xb);
-    const float mu6 = rho * fmaf(xb, c[F_TR(2)], -c[F_TR(0)]);
-    const float mv6 = rho * fmaf(yb, c[F_TR(2)], -c[F_TR(1)]);
     // pu = Guu mu + Guv mv ; pv = Guv mu + Gvv mv
     const float2 pu01 = mul2(rho, GA);                               // (Guu rho, Guv rho)
     const float pv1 = Gvv * rho;
     const float2 pu23 = fma2(Guu, mu23, mul2(Guv, mv23)), pv23 = fma2(Guv, mu23, mul2(Gvv, mv23));
     const float2 pu45 = fma2(Guu, mu45, mul2(Guv, mv45)), pv45 = fma2(Guv, mu45, mul2(Gvv, mv45));
-    const float2 p6 = fma2(mu6, GA, mul2(mv6, GB));                  // (pu6, pv6)
 
-    // pose block, upper triangle
-    A.a00 = fma2(rho, pu01, A.a00);
-    A.a02 = fma2(rho, pu23, A.a02);
-    A.a04 = fma2(rho, pu45, A.a04);
-    A.a11 = fmaf(rho, pv1, A.a11);
-    A.a12 = fma2(rho, pv23, A.a12);
-    A.a14 = fma2(rho, pv45, A.a14);
-    A.a22 = fma2(mu23.x, pu23, fma2(mv23.x, pv23, A.a22));
-    A.a24 = fma2(mu23.x, pu45, fma2(mv23.x, pv45, A.a24));
+    // rows 0..2 of the pose block and g_0..g_3: per run (the segment's depth column follows from them)
+    S.a00 = fma2(rho, pu01, S.a00);
+    S.a02 = fma2(rho, pu23, S.a02);
+    S.a04 = fma2(rho, pu45, S.a04);
+    S.a11 = fmaf(rho, pv1, S.a11);
+    S.a12 = fma2(rho, pv23, S.a12);
+    S.a14 = fma2(rho, pv45, S.a14);
+    S.a22 = fma2(mu23.x, pu23, fma2(mv23.x, pv23, S.a22));
+    S.a24 = fma2(mu23.x, pu45, fma2(mv23.x, pv45, S.a24));
+    S.g01 = fma2(rho, H, S.g01);
+    S.g23 = fma2(hu, mu23, fma2(hv, mv23, S.g23));
+    // rotation block, g_4, g_5, cost: per warp
     A.a33 = fmaf(mu23.y, pu23.y, fmaf(mv23.y, pv23.y, A.a33));
     A.a34 = fma2(mu23.y, pu45, fma2(mv23.y, pv45, A.a34));
     A.a44 = fma2(mu45.x, pu45, fma2(mv45.x, pv45, A.a44));
     A.a55 = fmaf(mu45.y, pu45.y, fmaf(mv45.y, pv45.y, A.a55));
-    // g_p = J^T W r
-    A.g01 = fma2(rho, H, A.g01);
-    A.g23 = fma2(hu, mu23, fma2(hv, mv23, A.g23));
     A.g45 = fma2(hu, mu45, fma2(hv, mv45, A.g45));
     A.cost += cost;
-    // depth column of this tile's segment
-    S.b01 = fma2(rho, p6, S.b01);
-    S.b23 = fma2(p6.x, mu23, fma2(p6.y, mv23, S.b23));
-    S.b45 = fma2(p6.x, mu45, fma2(p6.y, mv45, S.b45));
-    S.d = fmaf(mu6, p6.x, fmaf(mv6, p6.y, S.d));
-    S.gd = fmaf(mu6, hu, fmaf(mv6, hv, S.gd));
 }
 
 // ---- gradient mode, packed ------------------------------------------------------------------------

@@ -111,7 +111,7 @@ class AlignmentBatch:
         self.d_seg_cnt = torch.from_numpy(seg_cnt).to(dev)
         # workspaces / outputs
         self.ctas = lib.spb_gn_ctas(self.max_tiles, n)
-        self.work_stride = self.ctas * 47 + self.max_tiles * 10
+        self.work_stride = int(lib.spb_gn_work_stride(self.max_tiles, n))
         self.work = torch.empty(n * self.work_stride, dtype=torch.float32, device=dev)
         self.gn_pair = torch.zeros((n, nat.GN_PAIR_NOUT), dtype=torch.float32, device=dev)
         self.gn_seg = torch.zeros((self.seg_total, nat.GN_SEG_NOUT), dtype=torch.float32, device=dev)

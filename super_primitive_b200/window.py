@@ -146,7 +146,7 @@ class MappingWindows:
         self.d_geoms = _struct_array_to_device(garr, dev)
         self.d_pairs = _struct_array_to_device(parr, dev)
         self.ctas = lib.spb_gn_ctas(self.max_tiles, E)
-        self.work_stride = self.ctas * 47 + self.max_tiles * 10
+        self.work_stride = int(lib.spb_gn_work_stride(self.max_tiles, E))
         self.work = torch.empty(E * self.work_stride, dtype=torch.float32, device=dev)
         self.c = nat.SpbWindow(self.n_windows, F, E, lay['seg_total'],
                                *(self._idx[n].data_ptr() for n in ('win_frame_off', 'win_edge_off', 'edge_src', 'edge_trg',
