@@ -412,52 +412,22 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
 // ------------------------------------------------------------------------------------------------
 // Hot-path body: per-warp bulk-async pipelines (see spb_fast.cuh).  grid = (ctas_per_pair, pairs)
 //   part_pair : [cta][NACC]      part_seg : [tile][NSEG]
-//
-// A warp owns GROUPS of SPB_GROUP consecutive tiles (the warps of a CTA take adjacent groups, CTAs stride over the
-// pair).  The per-segment partial sums are reduced across the warp once per run of same-segment tiles inside a
-// group (a tile never straddles segments, a group may) instead of once per tile: the 8-value butterfly and its
-// store are ~70 of the ~150 instructions a lane spends per tile outside the point loop.  The run's sum lands in
-// the slot of its last tile, the other slots of the run receive zeros, so the finalize kernels are unchanged.
-//
-// SPB_TOUCH: the four bilinear taps are the only global loads of a point and the first touch of a target row by
-// an SM pays L2 / HBM latency.  Successive points of a lane (32 points apart in the segment's row-major order)
-// move by a nearly constant texel offset, so after consuming point j the lane touches the cache line it expects
-// point j+1 to need (2 off_j - off_{j-1}, bottom row) with a plain 4-byte load into a register nobody reads: the
-// line is in L1 one point-time (~1.5 k cycles) before the real taps ask for it.  (`prefetch.global.L1` lands the
-// line in L2 only on this part -- measured in round 1, profiles/README.md.)
+// The warps of a CTA take adjacent tiles (their target footprints share L1 lines), CTAs stride over the pair.
+// Measured and dropped in round 2 (profiles/README.md, visit r02a): groups of 2-8 consecutive tiles per warp with one
+// partial-sum reduction per same-segment run (GN unchanged, gradient kernel slower: L1 locality), and touching the
+// next point's predicted target row ahead of time with a 4-byte cp.async (the gathers already keep the L1 data path
+// 57 % busy; one more L1 access per point costs more than the latency it hides: l1tex 87 %, kernel 12 % slower).
 // ------------------------------------------------------------------------------------------------
-#ifndef SPB_GROUP
-#define SPB_GROUP 4                             // tiles per warp group (power of two)
-#endif
-#ifndef SPB_TOUCH
-#define SPB_TOUCH 1                             // 0: off, 1: touch the predicted bottom-row line, 2: both rows
-#endif
-
-// asynchronous 4-byte copy global -> a scratch word in shared memory (SASS LDGSTS): allocates the line in L1 like
-// any cached load, has no destination register (a plain load whose result is dead is removed by ptxas) and is never
-// waited for
-__device__ __forceinline__ void touch_line(const float4* p, uint32_t sink) {
-    asm volatile("cp.async.ca.shared.global.L2::256B [%0], [%1], 4;" ::"r"(sink), "l"(p) : "memory");
-}
-
 template <int MODE, int NP, bool AFF>
 __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair& pr, float irls_eps,
                                                 float* __restrict__ part_pair, float* __restrict__ part_seg) {
     constexpr int NACC = Sizes<MODE, NP>::NACC;
     constexpr int NSEG = Sizes<MODE, NP>::NSEG;
-    constexpr int GS = SPB_GROUP;
     extern __shared__ __align__(128) uint32_t s_dyn[];
     __shared__ __align__(16) float s_ctx[F_N];
     __shared__ float s_shift[SPB_NSHIFT];
     __shared__ float s_red[SPB_WARPS * NACC];
-#if SPB_TOUCH
-    __shared__ uint32_t s_sink[4];                          // landing word of the touch copies (never read)
-    const uint32_t sink = smem_u32(s_sink);
-#endif
-    const int lane = threadIdx.x & 31;
-    // broadcast from lane 0: tells the compiler the warp index -- and with it the tile / slot / phase bookkeeping of
-    // the loop below -- is warp-uniform, so it can live in uniform registers instead of the 80 vector registers
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* ring = s_dyn + warp * (SPB_WSTAGES * SPB_SLOT_WORDS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + SPB_WARPS * SPB_WSTAGES * SPB_SLOT_WORDS) + warp * SPB_WSTAGES;
 
@@ -472,15 +442,10 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     __syncthreads();
     const float* c = s_ctx;
 
-    const int n_tiles = g.n_tiles;
-    const int WS = gridDim.x * SPB_WARPS * GS;             // tile stride between two groups of this warp
-    const int t_first = (blockIdx.x * SPB_WARPS + warp) * GS;
+    const int WS = gridDim.x * SPB_WARPS;                  // tile stride of this warp
+    const int t_first = blockIdx.x * SPB_WARPS + warp;
+    const int t_end = g.n_tiles;
     const uint32_t* pack = pr.tile_pack;
-    // successor of tile t in this warp's sequence (>= n_tiles: none)
-    auto next_tile = [&](int t) {
-        const int tn = t + 1;
-        return ((tn & (GS - 1)) != 0 && tn < n_tiles) ? tn : (tn - 1) - ((tn - 1) & (GS - 1)) + WS;
-    };
 
     // producer (lane 0): ONE bulk copy brings the whole tile block (header + uv + logd + r + g + b)
     auto issue = [&](int t, int slot) {
@@ -489,17 +454,15 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
         bulk_g2s(smem_u32(ring + slot * SPB_SLOT_WORDS), pack + (size_t)t * SPB_PACK_WORDS, SPB_PACK_WORDS * 4u, bar);
     };
     if (lane == 0) {
-        int t = t_first;
 #pragma unroll
         for (int s = 0; s < SPB_WSTAGES - 1; ++s) {
-            if (t < n_tiles) issue(t, s);
-            t = next_tile(t);
+            const int t = t_first + s * WS;
+            if (t < t_end) issue(t, s);
         }
     }
 
     const float4* trg = reinterpret_cast<const float4*>(pr.trg_rgba);
     const int Wl = pr.Wl;
-    [[maybe_unused]] const uint32_t last_texel = (uint32_t)(pr.Hl * Wl - 1);
     constexpr bool PACKED = (MODE == MODE_GN && NP == 6);   // FFMA2 formulation (spb_gn_packed.cuh)
     float acc[NACC];
 #pragma unroll
@@ -508,30 +471,25 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     pacc.zero();
     GradAcc gacc;
     gacc.zero();
-    float seg[NSEG];
-#pragma unroll
-    for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
-    GnSeg6 pseg;
-    pseg.zero();
 
     int slot = 0, fill = SPB_WSTAGES - 1;                  // slot consumed now / slot refilled now
     uint32_t phase = 0;
-    int t_ahead = t_first;                                 // tile the producer issues next
-#pragma unroll
-    for (int s = 0; s < SPB_WSTAGES - 1; ++s) t_ahead = next_tile(t_ahead);
-#if SPB_TOUCH
-    int off_prev = -1;                                     // texel offset of this lane's previous valid point in the run
-#endif
-    int t = t_first;
-    if (t < n_tiles) mbar_wait(smem_u32(bars + slot), phase);
-    while (t < n_tiles) {
-        if (lane == 0 && t_ahead < n_tiles) issue(t_ahead, fill);
-        t_ahead = next_tile(t_ahead);
+    for (int t = t_first; t < t_end; t += WS) {
+        if (lane == 0) {
+            const int tn = t + (SPB_WSTAGES - 1) * WS;
+            if (tn < t_end) issue(tn, fill);
+        }
+        mbar_wait(smem_u32(bars + slot), phase);
         const uint32_t* sl = ring + slot * SPB_SLOT_WORDS;
         const int sidx = (int)sl[0];
         const float shift = (sidx < SPB_NSHIFT) ? s_shift[sidx] : (__ldg(pr.k + sidx) - __ldg(g.seg_lkp + sidx));
         const uint32_t* s_uv = sl + 4;
         const float* s_f = reinterpret_cast<const float*>(sl + 4);
+        float seg[NSEG];
+#pragma unroll
+        for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
+        GnSeg6 pseg;
+        pseg.zero();
         // padding entries of a partial tile are zero words: uv bit 31 clear => invalid, no bounds test needed
         SPB_PRAGMA_UNROLL(SPB_UNROLL)
         for (int j = 0; j < SPB_PPT; ++j) {
@@ -542,19 +500,6 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
             if (ok) {
                 Taps4 tp;
                 load_taps(trg, Wl, q.off, tp);
-#if SPB_TOUCH
-                {
-                    // where this lane's next point (32 points on) is expected: linear extrapolation of the texel offset,
-                    // bottom row.  Out-of-image predictions (and the first point of a run, off_prev = -1) clamp to the
-                    // last texel: a harmless touch.
-                    const uint32_t pred = min((uint32_t)(2 * q.off - off_prev + Wl), last_texel);
-                    touch_line(trg + pred, sink);
-#if SPB_TOUCH == 2
-                    touch_line(trg + (pred >= (uint32_t)Wl ? pred - Wl : 0u), sink);
-#endif
-                }
-                off_prev = q.off;
-#endif
                 const float i0 = s_f[2 * SPB_TILE + i], i1 = s_f[3 * SPB_TILE + i], i2 = s_f[4 * SPB_TILE + i];
                 if constexpr (MODE == MODE_GRAD)
                     point_grad_packed<AFF>(c, tp, q, i0, i1, i2, gacc, seg[0]);
@@ -564,37 +509,11 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
                     point_gn<NP, NACC, NSEG>(c, tp, q, i0, i1, i2, irls_eps, acc, seg);
             }
         }
+        if constexpr (PACKED) pseg.store(seg);
+        tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
         __syncwarp();                                      // every lane is done with this slot
-        // this warp's next tile, its ring slot, and whether it continues the same-segment run (its header says)
-        const int tn = t + 1;
-        const bool group_end = ((tn & (GS - 1)) == 0) || tn >= n_tiles;
-        const int t_next = group_end ? (t - (t & (GS - 1))) + WS : tn;
         fill = slot;
         if (++slot == SPB_WSTAGES) { slot = 0; phase ^= 1u; }
-        bool flush = group_end;
-        if (t_next < n_tiles) {
-            mbar_wait(smem_u32(bars + slot), phase);
-            if constexpr (GS > 1) {
-                if (!group_end) flush = (int)ring[slot * SPB_SLOT_WORDS] != sidx;
-            }
-        }
-        if (flush) {
-            if constexpr (PACKED) {
-                pseg.store(seg);
-                pseg.zero();
-            }
-            tile_reduce_store<NSEG>(seg, part_seg + (size_t)t * NSEG, lane);
-            if constexpr (!PACKED) {
-#pragma unroll
-                for (int i = 0; i < NSEG; ++i) seg[i] = 0.f;
-            }
-#if SPB_TOUCH
-            off_prev = -1;
-#endif
-        } else if constexpr (GS > 1) {
-            if (lane < NSEG) part_seg[(size_t)t * NSEG + lane] = 0.f;
-        }
-        t = t_next;
     }
     if constexpr (PACKED) pacc.store(acc);
     if constexpr (MODE == MODE_GRAD) gacc.store(acc);
@@ -982,11 +901,10 @@ static int sm_count() {
 }
 
 static inline int ctas_for(int n_tiles, int n_pairs, int occ) {
-    // every warp streams a strided set of tile groups through its own ring.  Size the grid to a whole number of waves
+    // every warp streams a strided set of tiles through its own ring.  Size the grid to a whole number of waves
     // of the kernel's occupancy (`occ` CTAs/SM): ~4 waves over all pairs, rounded DOWN so the last wave is nearly
     // full (a 5.3-wave grid wastes a third of its last wave).
-    const int n_groups = (n_tiles + SPB_GROUP - 1) / SPB_GROUP;
-    const int max_ctas = (n_groups + SPB_WARPS - 1) / SPB_WARPS;
+    const int max_ctas = (n_tiles + SPB_WARPS - 1) / SPB_WARPS;
     const int slots = sm_count() * occ;
     if (n_pairs < 1) n_pairs = 1;
     if ((long long)n_pairs * max_ctas <= slots) return max_ctas;

@@ -173,15 +173,25 @@ RGBA_CACHE_SIZE = 32
 
 
 def geometry_of(kf) -> CompactGeometry:
-    """Compact geometry of a keyframe, cached on the identity/version of its geometry tensors."""
+    """Compact geometry of a keyframe, cached on the identity/version of its geometry tensors (masks, log-depth,
+    keypoints).  The intrinsics are a 9-float VALUE of the call, not part of the key: `keyframe_pyramid` gives every
+    level its own `K.clone()` (image/keyframe.py:125-146), and with `geo_down=False` -- every caller -- all levels share
+    one geometry.  When a hit arrives with a different K tensor its values are copied into the geometry's own device
+    buffer (stream-ordered, no host sync), so the three compaction passes and their one host sync run once per keyframe."""
     reg, ld, kp, K = kf.keypoint_regions, kf.get_logdepth(), kf.keypoints, kf.K
-    key = (id(reg), reg._version, id(ld), ld._version, id(kp), kp._version, id(K), K._version)
+    key = (id(reg), reg._version, id(ld), ld._version, id(kp), kp._version)
     hit = _GEOM_CACHE.get(key)
-    if hit is not None and hit[0]() is reg and hit[1]() is ld and hit[2]() is kp and hit[3]() is K:
+    if hit is not None and hit[0]() is reg and hit[1]() is ld and hit[2]() is kp:
         _GEOM_CACHE.move_to_end(key)
-        return hit[4]
+        g = hit[3]
+        kref, kver = g._K_src
+        if kref() is not K or kver != K._version:
+            g.K.copy_(_f32c(K).reshape(g.K.shape), non_blocking=True)
+            g._K_src = (weakref.ref(K), K._version)
+        return g
     g = CompactGeometry(reg, ld, kp, K)
-    _GEOM_CACHE[key] = (weakref.ref(reg), weakref.ref(ld), weakref.ref(kp), weakref.ref(K), g)
+    g._K_src = (weakref.ref(K), K._version)
+    _GEOM_CACHE[key] = (weakref.ref(reg), weakref.ref(ld), weakref.ref(kp), g)
     while len(_GEOM_CACHE) > GEOM_CACHE_SIZE:
         _GEOM_CACHE.popitem(last=False)
     return g

@@ -74,5 +74,24 @@ def assert_close(a, b, tol, what=""):
     assert e <= tol, f"{what}: scale-relative error {e:.3e} > {tol:.1e}"
 
 
+def assert_close_elem(a, b, tol, what="", floor=1e-3):
+    """ELEMENT-wise bar: |a - b| <= tol * max(|b|, floor * max|b|) for every entry -- a small per-segment gradient
+    cannot hide behind the largest one (the scale-relative bar above lets it)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.abs(b), floor * max(np.abs(b).max(), 1e-30))
+    e = np.abs(a - b) / scale
+    i = int(np.argmax(e))
+    assert e.max() <= tol, (f"{what}: element {np.unravel_index(i, e.shape)} off by {e.max():.3e} of its own "
+                            f"magnitude (got {a.flat[i]:.6e}, want {b.flat[i]:.6e}) > {tol:.1e}")
+
+
+def elem_err(a, b, floor=1e-3):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.abs(b), floor * max(np.abs(b).max(), 1e-30))
+    return float((np.abs(a - b) / scale).max())
+
+
 def to_np(x):
     return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)

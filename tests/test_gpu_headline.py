@@ -1,0 +1,337 @@
+"""GPU: parity on the shapes and loops the headline numbers are quoted on.
+
+* BASELINE config 2 (640x480, 64 overlapping segments, 3-level pyramid): `photomeric_cost`, `photomeric_cost_batch`
+  (B = 4) and `photomeric_cost_precomputed` through the Python surface -> C ABI against oracle/ref_port.py (pinned bit
+  for bit to the live reference) in float64 and float32, with an ELEMENT-wise bar on every gradient entry.
+* the callers' loops against what the reference's own caller code left behind (tests/golden/sfm_run.npz, tracker.npz,
+  mapping_window.npz -- `SfM.run`, `Odometery.track_frame`, `Odometery.mapping` executed unmodified,
+  tests/golden/make_golden_callers.py): the drop-in `photomeric_cost` loop, `AlignmentBatch.adam_step`, `MappingWindows`.
+* the GN/LM extension against the reference's optimiser: both minimise the same L1 objective, so run to convergence they
+  must meet at the same (pose, log-depth).
+
+Bars.  The float32 reference is itself only an approximation of its float64 evaluation: sign(r) flips of near-zero
+residuals move a per-segment gradient by ~1/points-per-segment, so where the float32 port's own distance to float64 is
+above 1e-4 the bar is twice that distance (stated per assertion), never looser than 1e-3.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.common import CFG0, assert_close, assert_close_elem, elem_err, rel_err, to_np
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _leaf(t):
+    return t.clone().requires_grad_(True)
+
+
+def _f64(kf):
+    from super_primitive_b200.keyframe import KeyFrame
+    c = lambda t: None if t is None else (t.double() if t.is_floating_point() else t)   # noqa: E731
+    return KeyFrame(c(kf.image), c(kf.K), c(kf.logdepth_perseg), c(kf.keypoints), kf.keypoint_regions, c(kf.K_img))
+
+
+def _elem_bar(got, ref32, ref64, what, tol=1e-4):
+    """element-wise: GPU vs float64 within max(tol, 2 x the float32 reference's own element-wise distance), <= 1e-3."""
+    e_gpu, e_ref = elem_err(got, ref64), elem_err(ref32, ref64)
+    bar = min(max(tol, 2.0 * e_ref), 1e-3)
+    assert e_gpu <= bar, f"{what}: GPU vs float64 {e_gpu:.2e} (element-wise), float32 reference {e_ref:.2e}, bar {bar:.1e}"
+    return e_gpu, e_ref
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 2: 640x480, 64 segments, 3 levels
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c2():
+    from super_primitive_b200 import synthetic as syn
+    H, W, N = 480, 640, 64
+    src, trg, k0, pose0 = syn.two_frame_problem(H, W, N, kind="overlap", seed=0, noise=0.01)     # bench.py's generator
+    g = torch.Generator().manual_seed(5)
+    k0 = k0 + 0.05 * torch.randn(N, generator=g)
+    pose0 = syn.small_pose(0.02, -0.004, 0.006, 0.003, -0.004, 0.002)
+    return dict(src=syn.keyframe_pyramid(src, 0, 3), trg=syn.keyframe_pyramid(trg, 0, 3), k0=k0, pose0=pose0, N=N)
+
+
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_c2_single_target_against_oracle(c2, level):
+    from oracle import ref_port as port
+    from super_primitive_b200 import dense_optim as do
+    s, t, k0, pose0 = c2['src'][level], c2['trg'][level], c2['k0'], c2['pose0']
+    k64, p64 = _leaf(k0.double()), _leaf(pose0.double())
+    r64 = port.cost_single(_f64(s), _f64(t), k64, p64, CFG0)
+    r64['residual'].mean().backward()
+    k32, p32 = _leaf(k0), _leaf(pose0)
+    r32 = port.cost_single(s, t, k32, p32, CFG0)
+    r32['residual'].mean().backward()
+    kg, pg = _leaf(k0.cuda()), _leaf(pose0.cuda())
+    out = do.photomeric_cost(s.to("cuda"), t.to("cuda"), kg, pg, CFG0)
+    out['residual'].mean().backward()
+    assert_close(to_np(out['residual']), to_np(r64['residual']), 2e-5, f"C2 L{level} cost")
+    _elem_bar(to_np(kg.grad), to_np(k32.grad), to_np(k64.grad), f"C2 L{level} d/dk (64 entries)")
+    _elem_bar(to_np(pg.grad)[:3], to_np(p32.grad)[:3], to_np(p64.grad)[:3], f"C2 L{level} d/dpose")
+    assert float(to_np(pg.grad)[3].max()) == 0.0
+
+
+def test_c2_batch_of_four_targets_against_oracle(c2):
+    from oracle import ref_port as port
+    from super_primitive_b200 import dense_optim_batch as dob, synthetic as syn
+    B, level = 4, 2
+    s = c2['src'][level]
+    H, W = s.keypoint_regions.shape[1:]
+    trgs = [syn.keyframe_pyramid(syn.make_keyframe(H, W, c2['N'], shift=(1.5 + 0.5 * j, 1.0 - 0.4 * j), noise=0.01,
+                                                   seed=50 + j, supporting=True), 0, 3)[level] for j in range(B)]
+    imgs = torch.stack([t.image for t in trgs])
+    Ks = torch.stack([t.K for t in trgs])
+    poses0 = torch.stack([syn.small_pose(0.02 - 0.005 * j, 0.003 * j, -0.002 * j, 0.003, -0.002 * j, 0.002)
+                          for j in range(B)])
+    a_s, a_t = torch.tensor([0.03, -0.01]), torch.tensor([[0.01 * j, 0.02 - 0.01 * j] for j in range(B)])
+    k0 = c2['k0']
+    k64, p64, as64, at64 = _leaf(k0.double()), _leaf(poses0.double()), _leaf(a_s.double()), _leaf(a_t.double())
+    r64 = port.cost_batch(_f64(s), imgs.double(), Ks.double(), k64, p64, CFG0, (as64, at64))
+    r64['residual'].mean().backward()
+    k32, p32, as32, at32 = _leaf(k0), _leaf(poses0), _leaf(a_s), _leaf(a_t)
+    r32 = port.cost_batch(s, imgs, Ks, k32, p32, CFG0, (as32, at32))
+    r32['residual'].mean().backward()
+    kg, pg, asg, atg = _leaf(k0.cuda()), _leaf(poses0.cuda()), _leaf(a_s.cuda()), _leaf(a_t.cuda())
+    out = dob.photomeric_cost_batch(s.to("cuda"), imgs.cuda(), Ks.cuda(), kg, pg, CFG0, (asg, atg))
+    out['residual'].mean().backward()
+    assert_close_elem(to_np(out['residual']), to_np(r64['residual']), 2e-5, "C2 batch cost")
+    _elem_bar(to_np(kg.grad), to_np(k32.grad), to_np(k64.grad), "C2 batch d/dk")
+    _elem_bar(to_np(pg.grad)[:, :3], to_np(p32.grad)[:, :3], to_np(p64.grad)[:, :3], "C2 batch d/dposes")
+    _elem_bar(to_np(asg.grad), to_np(as32.grad), to_np(as64.grad), "C2 batch d/d aff_src")
+    _elem_bar(to_np(atg.grad), to_np(at32.grad), to_np(at64.grad), "C2 batch d/d aff_trg")
+
+
+def test_c2_precomputed_tracking_against_oracle(c2):
+    from oracle import ref_port as port
+    from super_primitive_b200 import dense_optim as do
+    level = 2
+    s, t, k0, pose0 = c2['src'][level], c2['trg'][level], c2['k0'], c2['pose0']
+    a_s, a_t = torch.tensor([0.02, 0.01]), torch.tensor([-0.01, 0.02])
+    with torch.no_grad():
+        pre = do.unproject_kf(s.to("cuda"), k0.cuda())
+        pre32 = port.lift_keyframe(s, k0)
+        pre64 = port.lift_keyframe(_f64(s), k0.double())
+    assert pre['src_pts'].shape == pre32['src_pts'].shape
+    assert_close(to_np(pre['src_pts']), to_np(pre64['src_pts']), 1e-6, "lifted points")
+    p64, at64 = _leaf(pose0.double()), _leaf(a_t.double())
+    r64 = port.cost_precomputed(pre64, _f64(t), p64, CFG0, (a_s.double(), at64))
+    r64['residual'].mean().backward()
+    p32, at32 = _leaf(pose0), _leaf(a_t)
+    r32 = port.cost_precomputed(pre32, t, p32, CFG0, (a_s, at32))
+    r32['residual'].mean().backward()
+    pg, atg = _leaf(pose0.cuda()), _leaf(a_t.cuda())
+    out = do.photomeric_cost_precomputed(pre, t.to("cuda"), pg, CFG0, (a_s.cuda(), atg))
+    out['residual'].mean().backward()
+    assert_close(to_np(out['residual']), to_np(r64['residual']), 2e-5, "C2 tracking cost")
+    _elem_bar(to_np(pg.grad)[:3], to_np(p32.grad)[:3], to_np(p64.grad)[:3], "C2 tracking d/dpose")
+    _elem_bar(to_np(atg.grad), to_np(at32.grad), to_np(at64.grad), "C2 tracking d/d aff_trg")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the callers' loops against the reference's own caller results
+# ---------------------------------------------------------------------------------------------------------------------
+def _sfm_setup():
+    from super_primitive_b200 import synthetic as syn
+    z = np.load(os.path.join(HERE, "golden", "sfm_run.npz"))
+    c = {key[4:]: z[key].item() for key in z.files if key.startswith("cfg_")}
+    src = syn.make_keyframe(c['H'], c['W'], c['N'], kind=c['kind'], seed=c['seed'], noise=c['noise'])
+    trgs = [syn.make_keyframe(c['H'], c['W'], c['N'], shift=(2.0 + j, 1.0 - 0.5 * j), noise=c['noise'],
+                              seed=c['seed'] + 1 + j, supporting=True) for j in range(c['n_supp'])]
+    return z, c, syn.keyframe_pyramid(src, 0, c['levels']), [syn.keyframe_pyramid(t, 0, c['levels']) for t in trgs]
+
+
+def _dropin_sfm_loop(src_levels, trg_levels, k0, T0s, iters_per_level):
+    """odometery/two_frame_sfm.py:127-206 with the drop-in `photomeric_cost` in place of the reference's: same optimiser,
+    same groups, same skipped first step; the twist exponential is the test-side stand-in of the absent lietorch."""
+    from super_primitive_b200 import dense_optim as do
+    dev = "cuda"
+    k = k0.to(dev).clone().requires_grad_(True)
+    deltas = [torch.zeros(1, 6, device=dev, requires_grad=True) for _ in T0s]
+    opt = torch.optim.Adam([{'params': k, 'lr': 1e-3}, {'params': deltas, 'lr': 1e-2}], lr=1e-3)
+    src_g = [s.to(dev) for s in src_levels]
+    trg_g = [[t.to(dev) for t in lv] for lv in trg_levels]
+    T0g = [T.to(dev) for T in T0s]
+    losses, count = [], 0
+
+    def exp_dev(d):       # the oracle's retraction (matrix exponential of the twist matrix), on the device
+        tau, phi = d[:3], d[3:]
+        z = torch.zeros((), device=dev)
+        return torch.linalg.matrix_exp(torch.stack([torch.stack([z, -phi[2], phi[1], tau[0]]),
+                                                    torch.stack([phi[2], z, -phi[0], tau[1]]),
+                                                    torch.stack([-phi[1], phi[0], z, tau[2]]),
+                                                    torch.stack([z, z, z, z])]))
+
+    for lvl in range(len(src_levels)):
+        for _ in range(iters_per_level):
+            per = []
+            for j in range(len(T0s)):
+                pose = exp_dev(deltas[j][0]) @ T0g[j]
+                res = do.photomeric_cost(src_g[lvl], trg_g[j][lvl], k, pose, CFG0)
+                per.append(torch.mean(torch.abs(res['residual'])))
+            loss = torch.sum(torch.stack(per))
+            if count > 0:
+                loss.backward()
+                opt.step()
+                opt.zero_grad()
+            count += 1
+            losses.append(float(loss.detach()))
+    return k.detach().cpu(), torch.stack([d.detach()[0].cpu() for d in deltas]), losses
+
+
+def test_dropin_sfm_loop_first_iterations_track_the_reference_loop():
+    """60 iterations per level (both levels) of the reference's two-frame loop: the drop-in trajectory stays on the
+    oracle's (oracle/adam_loop.sfm_adam reproduces the reference's `SfM.run` bit for bit over 1000 iterations,
+    tests/test_callers_golden_cpu.py)."""
+    from oracle import adam_loop
+    z, c, src_levels, trg_levels = _sfm_setup()
+    T0s = [torch.from_numpy(T) for T in z["T0s"]]
+    k0 = torch.from_numpy(z["k0"])
+    n = 60
+    want = adam_loop.sfm_adam(src_levels, trg_levels, k0, T0s, n)
+    k, deltas, losses = _dropin_sfm_loop(src_levels, trg_levels, k0, T0s, n)
+    moved = float(np.abs(to_np(want['k']) - z["k0"]).max())
+    assert moved > 0.03                                                  # ~ lr * iterations: a real trajectory
+    np.testing.assert_allclose(losses, want['losses'], rtol=2e-4)
+    np.testing.assert_allclose(to_np(k), to_np(want['k']), atol=1e-4)
+    np.testing.assert_allclose(to_np(deltas), np.stack([to_np(d) for d in want['deltas']]), atol=1e-4)
+
+
+def test_dropin_sfm_loop_reaches_the_reference_result():
+    """The whole run (2 levels x 500 iterations) against what the reference's `SfM.run` left (tests/golden/sfm_run.npz).
+    Adam divides by sqrt(v): float32-level gradient differences are amplified over 1000 steps, so the end state is
+    compared at 2e-3 (seeds moved by 0.27, increments by ~0.1) and the final loss at 1 %."""
+    z, c, src_levels, trg_levels = _sfm_setup()
+    T0s = [torch.from_numpy(T) for T in z["T0s"]]
+    k, deltas, losses = _dropin_sfm_loop(src_levels, trg_levels, torch.from_numpy(z["k0"]), T0s, 500)
+    assert abs(losses[0] - float(z["loss_first"])) <= 2e-5 * float(z["loss_first"])
+    assert abs(losses[-1] - float(z["loss_last"])) <= 1e-2 * float(z["loss_last"])
+    np.testing.assert_allclose(to_np(k), z["k"], atol=2e-3)
+    np.testing.assert_allclose(to_np(deltas), z["deltas"], atol=2e-3)
+
+
+def test_adam_step_reaches_the_reference_tracker_result():
+    """`AlignmentBatch.adam_step` (pose increment + target brightness, seeds held) against what the reference's own
+    `Odometery.track_frame` left (tests/golden/tracker.npz)."""
+    from super_primitive_b200 import synthetic as syn
+    from super_primitive_b200.solver import AlignmentBatch, make_problem
+    z = np.load(os.path.join(HERE, "golden", "tracker.npz"))
+    c = {key[4:]: z[key].item() for key in z.files if key.startswith("cfg_")}
+    src, trg, k0, pose0 = syn.two_frame_problem(c['H'], c['W'], c['N'], kind=c['kind'], seed=c['seed'], noise=c['noise'])
+    a_s, a_t0 = torch.from_numpy(z["aff_src"]), torch.from_numpy(z["aff_trg0"])
+    batch = AlignmentBatch([make_problem(src.to("cuda"), trg.to("cuda").image, trg.K.cuda(), pose0.cuda(), k0.cuda(),
+                                         aff_src=a_s.cuda(), aff_trg=a_t0.cuda())], with_affine=True)
+    for _ in range(c['iters']):
+        batch.adam_step(lr_pose=c['lr'], lr_k=0.0, lr_aff=5e-3)
+    torch.cuda.synchronize()
+    moved = float(np.abs(z["rel_pose"] - pose0.numpy()).max())
+    err = float(np.abs(to_np(batch.poses_matrix()[0]) - z["rel_pose"]).max())
+    assert err <= 1e-4 and err <= 0.02 * moved, f"pose off by {err:.2e} after moving {moved:.2e}"
+    np.testing.assert_allclose(to_np(batch.aff_trg[0]), z["aff_trg"], atol=1e-4)
+    assert torch.equal(batch.k_of(0).cpu(), k0)
+
+
+def test_mapping_windows_reach_the_reference_mapping_result():
+    """`MappingWindows` against what the reference's own `Odometery.mapping` left after 8 iterations of a 3-keyframe
+    window with supporting frames and brightness terms (tests/golden/mapping_window.npz)."""
+    from super_primitive_b200 import synthetic as syn
+    from super_primitive_b200.window import MappingWindows
+    from tests.test_gpu_window import _to_cuda
+    z = np.load(os.path.join(HERE, "golden", "mapping_window.npz"))
+    shape = {key[6:]: z[key].item() for key in z.files if key.startswith("shape_")}
+    w = syn.mapping_window(**shape)
+    lr = z["lr"]
+    mw = MappingWindows([_to_cuda(w)])
+    for _ in range(int(z["iters"])):
+        mw.step(lr_pose=float(lr[0]), lr_k=float(lr[1]), lr_aff=float(lr[2]), stop_tol=float(z["stop_tol"]))
+    torch.cuda.synchronize()
+    assert to_np(mw.steps_done()).tolist() == [int(z["iters"])]
+    np.testing.assert_allclose(to_np(mw.poses()), z["T"], atol=2e-6)
+    for f in range(shape['n_kf']):
+        np.testing.assert_allclose(to_np(mw.seeds_of(f)), z["k"][f], atol=2e-5)
+    ok = ~np.isnan(z["aff"]).any(axis=1)
+    np.testing.assert_allclose(to_np(mw.frame_aff)[ok], z["aff"][ok], atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GN/LM (extension) vs the reference's optimiser: same objective, same optimum
+# ---------------------------------------------------------------------------------------------------------------------
+def test_gn_and_reference_adam_converge_to_the_same_optimum_c1():
+    """BASELINE config 1 shape (256x192, 8 segments).  The IRLS-GN/LM loop (irls_eps -> small) and the reference's Adam
+    loop (oracle/adam_loop.tracker_adam, learning rates decayed by hand so Adam settles instead of orbiting) minimise the
+    same L1 cost; both are run until the cost stops changing and must agree on pose and log-depth.  The measured gap is
+    printed; the bar is 1e-4 on the pose and the seeds."""
+    from oracle import adam_loop, ref_port as port
+    from super_primitive_b200 import synthetic as syn
+    from super_primitive_b200.solver import AlignmentBatch, make_problem
+    H, W, N = 192, 256, 8
+    T_true = syn.small_pose(0.02, -0.01, 0.005, 0.004, -0.006, 0.008)
+    src, trg, k_true = syn.planar_scene_pair(H, W, N, T_true, z0=2.0, kind="strips")
+    k0, pose0 = k_true + 0.03, torch.eye(4)
+    # --- GN/LM on the device, from the same start
+    batch = AlignmentBatch([make_problem(src.to("cuda"), trg.to("cuda").image, trg.K.cuda(), pose0.cuda(), k0.cuda())],
+                           irls_eps=1e-4)
+    prev = None
+    for it in range(400):
+        batch.gn_step()
+        if it % 20 == 19:
+            cost = float(batch.lm_state[0, 1])
+            if prev is not None and abs(prev - cost) <= 1e-9 * abs(cost):
+                break
+            prev = cost
+    torch.cuda.synchronize()
+    pose_gn, k_gn = to_np(batch.poses_matrix()[0]).astype(np.float64), to_np(batch.k_of(0)).astype(np.float64)
+    # --- the reference's optimiser (float64 oracle), continued from the GN result's neighbourhood would be circular:
+    # start it from the SAME initial point and let it run with decaying steps
+    res = dict(pose=pose0.double(), k=k0.double())
+    s64, t64 = _f64(src), _f64(trg)
+    for lr in (1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 3e-6):
+        res = adam_loop.tracker_adam(s64, t64, res['k'], res['pose'], 200, lr_pose=lr, lr_k=lr)
+    pose_ad, k_ad = to_np(res['pose']), to_np(res['k'])
+
+    def cost64(pose, k):
+        with torch.no_grad():
+            return float(port.cost_single(s64, t64, torch.from_numpy(k), torch.from_numpy(pose), CFG0)['residual'].mean())
+
+    c_gn, c_ad = cost64(pose_gn, k_gn), cost64(pose_ad, k_ad)
+    # monocular gauge: (k + s, e^s t) has the same cost for every s, so the optimum is a one-parameter family and the
+    # two optimisers stop at different members of it; compare after moving the GN result onto Adam's scale
+    s = float(np.mean(k_gn - k_ad))
+    k_al, t_al = k_gn - s, pose_gn[:3, 3] * math.exp(-s)
+    e_R = float(np.abs(pose_gn[:3, :3] - pose_ad[:3, :3]).max())
+    e_t = float(np.abs(t_al - pose_ad[:3, 3]).max())
+    e_k = float(np.abs(k_al - k_ad).max())
+    print(f"GN vs Adam optimum: |dR| {e_R:.2e}  |dt| {e_t:.2e}  |dk| {e_k:.2e} (scale gauge {s:+.4f})  "
+          f"cost GN {c_gn:.8f}  Adam {c_ad:.8f}  LM iterations {it + 1}")
+    # GN must be at least as good a minimiser of the reference's objective as the reference's own optimiser
+    assert c_gn <= c_ad * (1 + 1e-4), f"GN cost {c_gn} vs Adam {c_ad}"
+    assert e_R <= 1e-4 and e_t <= 1e-4 and e_k <= 1e-4, f"rotation {e_R:.2e}, translation {e_t:.2e}, seeds {e_k:.2e}"
+
+
+def test_all_pyramid_levels_share_one_compact_geometry():
+    """`keyframe_pyramid(geo_down=False)` clones K per level (image/keyframe.py:125-146): the geometry cache must not key
+    on the K tensor, or every level of every tracked frame re-runs the compaction and its host sync."""
+    from super_primitive_b200 import synthetic as syn
+    from super_primitive_b200.geometry import clear_caches, geometry_of
+    from super_primitive_b200.pyramid import keyframe_pyramid
+    clear_caches()
+    kf = syn.make_keyframe(96, 128, 6, kind="rects", seed=4, noise=0.01).to("cuda")
+    levels = keyframe_pyramid(kf, 0, 3)
+    assert len({id(lv.K) for lv in levels}) == 3                       # distinct K tensors, as in the reference
+    geoms = [geometry_of(lv) for lv in levels]
+    assert geoms[0] is geoms[1] is geoms[2]
+    # a keyframe with different intrinsics VALUES on the same geometry tensors: same geometry object, K refreshed
+    K2 = kf.K.clone()
+    K2[0, 0] *= 1.25
+    from super_primitive_b200.keyframe import KeyFrame
+    other = KeyFrame(kf.image, K2, kf.logdepth_perseg, kf.keypoints, kf.keypoint_regions, kf.K_img)
+    g2 = geometry_of(other)
+    assert g2 is geoms[0] and torch.equal(g2.K.reshape(3, 3), K2)
+    geometry_of(levels[0])
+    assert torch.equal(g2.K.reshape(3, 3), kf.K)
