@@ -45,7 +45,44 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="pairs per ingest launch group of the end-to-end arm")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2levels", "c3", "c4", "c5", "compaction"],
+                    help="c2 = the headline (BASELINE config 2, finest level); the others: bench_workloads.py")
+    ap.add_argument("--units", type=int, default=0, help="c3: problems per GPU; c4 / c5: units in total (0 = default)")
+    ap.add_argument("--segments", type=int, default=0, help="segments per keyframe of c3 / c4 / c5 (0 = the config's)")
+    ap.add_argument("--no-numa-pin", action="store_true", help="do not bind the rank to the CPUs next to its GPU")
     return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# host placement: a rank's pinned staging memory should live on the NUMA node its GPU hangs off
+# --------------------------------------------------------------------------------------------------
+def pin_rank_to_gpu_numa(local_rank, world):
+    """Bind this process to the CPUs local to its GPU's PCIe root (sysfs `local_cpulist`), split between the ranks that
+    share them, BEFORE the pinned arenas are allocated (first touch then places them on that node).  Round 1's 8-GPU
+    end-to-end arm ran every rank on NUMA node 0 and its per-GPU H2D rate fell from 54 to 21 GB/s.  Returns a dict for
+    the JSON line (what was found / done); never raises."""
+    info = {"pinned": False}
+    try:
+        prop = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bus
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        cpus = []
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus += list(range(int(a), int(b) + 1))
+            elif part:
+                cpus.append(int(part))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        info.update(pci=bus, numa_node=node, local_cpus=len(cpus), allowed_local_cpus=len(allowed))
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            info["pinned"] = True
+    except Exception as e:      # noqa: BLE001
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
 
 
 # --------------------------------------------------------------------------------------------------
@@ -167,8 +204,12 @@ class HostStaged:
         # SPB_E2E_LEAN=1 (tuning visits with a fused-ingest library only): skip the buffers the iteration does not read
         self.ingest = FrameIngest(problems, batch.geoms, lean=bool(os.environ.get("SPB_E2E_LEAN")))
         self.arena = self.ingest.host_arena()          # pinned arena a loader decodes the 8-bit frames into
+        # the odometry case: the source keyframe is resident, only the new (target) frame of every pair arrives
+        self.ingest_t = FrameIngest(problems, batch.geoms, target_only=True)
+        self.arena_t = self.ingest_t.host_arena()
         for i, p in enumerate(problems):
             self.ingest.fill(self.arena, i, p['src_u8'].cpu(), p['trg_u8'].cpu())
+            self.ingest_t.fill(self.arena_t, i, None, p['trg_u8'].cpu())
         self.chunk = max(1, int(chunk))                # pairs per ingest launch group (copy/compute overlap)
         self.chunk_events = [torch.cuda.Event() for _ in range((len(problems) + self.chunk - 1) // self.chunk)]
         self.consumed = []
@@ -180,19 +221,21 @@ class HostStaged:
         nbytes = lambda pairs: sum(t.numel() * t.element_size() for pr in pairs for t in pr)   # noqa: E731
         self.params_bytes = self.h_pose.numel() * 4 + self.h_k.numel() * 4
         self.h2d = {"u8": self.ingest.offsets[-1] + self.params_bytes,      # bytes actually copied (16-byte aligned frames)
+                    "u8t": self.ingest_t.offsets[-1] + self.params_bytes,
                     "raw": nbytes(self.raw_host) + self.params_bytes,
                     "packed": nbytes(self.packed_host) + self.params_bytes, "params": self.params_bytes}
         self.d2h = (self.o_pose.numel() + self.o_k.numel() + self.o_cost.numel()) * 4
         self.copy_stream = torch.cuda.Stream()
         self.events = [torch.cuda.Event() for _ in problems]
-        self.launches_per_step = {"u8": 3 * len(self.chunk_events) + 2, "raw": 3 * len(problems) + 2, "packed": 2,
-                                  "params": 2}
+        self.launches_per_step = {"u8": 3 * len(self.chunk_events) + 2, "u8t": 3 * len(self.chunk_events) + 2,
+                                  "raw": 3 * len(problems) + 2, "packed": 2, "params": 2}
 
     def step(self, mode="u8"):
         b = self.batch
         main = torch.cuda.current_stream()
-        if mode == "u8":
-            cs, ing, n = self.copy_stream, self.ingest, len(self.problems)
+        if mode in ("u8", "u8t"):
+            cs, n = self.copy_stream, len(self.problems)
+            ing, arena = (self.ingest, self.arena) if mode == "u8" else (self.ingest_t, self.arena_t)
             if len(self.consumed) != len(self.chunk_events):
                 self.consumed = [None] * len(self.chunk_events)
             with torch.cuda.stream(cs):
@@ -200,7 +243,7 @@ class HostStaged:
                     first = c * self.chunk
                     if self.consumed[c] is not None:
                         cs.wait_event(self.consumed[c])     # the previous step's ingest has read this part of the staging buffer
-                    ing.upload(self.arena, first, min(n, first + self.chunk) - first)      # one copy per chunk
+                    ing.upload(arena, first, min(n, first + self.chunk) - first)      # one copy per chunk
                     ev.record(cs)
             for c, ev in enumerate(self.chunk_events):
                 main.wait_event(ev)
@@ -464,8 +507,15 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa = {"pinned": False, "skipped": True} if args.no_numa_pin else pin_rank_to_gpu_numa(local_rank, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    if args.workload != "c2":
+        import bench_workloads as bw
+        bw.RUNNERS[args.workload](bw.Ctx(args, rank, world, device, dist))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     from super_primitive_b200.shard import gather_results
 
     steps, warm = max(1, args.steps), max(3, args.warmup)
@@ -564,6 +614,7 @@ def main():
         p1.record()
         torch.cuda.synchronize()
         h2d_gbps = 5 * hs.ingest.offsets[-1] / (p0.elapsed_time(p1) * 1e-3) / 1e9
+        v_u8t = timed("u8t")            # informational: the odometry case, only the new frame of every pair travels
         v_raw = timed("raw")            # informational: frames converted to float32 on the host (the reference's image_tt)
         v_packed = timed("packed")      # informational: derived buffers uploaded instead of frames
         v_params = timed("params")      # informational: frames resident (as the reference keeps its KeyFrames)
@@ -576,6 +627,12 @@ def main():
                        "reference's dataset readers deliver them) + pose + seeds; on the device spb_ingest_u8 (image_tt, "
                        "RGBA target, cached source samples, tile-major level buffer; three launches per chunk of %d pairs, "
                        "overlapped with the remaining copies), one GN/LM iteration; D2H of poses, seeds and LM state" % hs.chunk,
+               "target_frame_only": {"value": v_u8t, "h2d_bytes_per_step": int(hs.h2d["u8t"]),
+                                     "frac_of_link": (hs.h2d["u8t"] * v_u8t / pairs_total) / 1e9 / h2d_gbps,
+                                     "what": "the odometry case (odometery/odometery.py:323-403): the source keyframe and "
+                                             "its derived buffers stay resident, only the 8-bit TARGET frame of every pair "
+                                             "+ pose + seeds travel"},
+               "numa": numa,
                "frames_f32": {"value": v_raw, "h2d_bytes_per_step": int(hs.h2d["raw"]),
                               "what": "frames converted to float32 on the host as the reference's image_tt does "
                                       "(12 bytes per pixel over PCIe), re-derived pair by pair"},

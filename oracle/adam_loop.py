@@ -40,8 +40,13 @@ def exp_se3(delta):
 def tracker_adam(src, trg, k0, pose0, iters, lr_pose=1e-2, lr_k=1e-3, lr_aff=5e-3, affine=None, opt_affine=False,
                  cost_config=None):
     """Runs `iters` iterations; returns dict(pose, k, aff_trg, costs[iters]) in the dtype of the inputs.
-    `affine` = (src (2,), trg (2,)) or None; the target terms are optimised when `opt_affine`."""
+    `affine` = (src (2,), trg (2,)) or None; the target terms are optimised when `opt_affine`.
+    `src` / `trg` may be lists of pyramid levels (coarse -> fine) with `iters` a list of the same length: the
+    reference's coarse-to-fine schedule (`for pyr_level ... for iter in range(steps[pyr_level])`,
+    odometery/odometery.py:376-384) with ONE optimiser across the levels."""
     cfg = cost_config or {'mode': 'colour', 'collect_stats': 0}
+    if not isinstance(src, (list, tuple)):
+        src, trg, iters = [src], [trg], [iters]
     dt = k0.dtype
     was = torch.is_grad_enabled()
     torch.set_grad_enabled(True)
@@ -58,17 +63,18 @@ def tracker_adam(src, trg, k0, pose0, iters, lr_pose=1e-2, lr_k=1e-3, lr_aff=5e-
                 groups.append({'params': [aff_t], 'lr': lr_aff})
         opt = torch.optim.Adam(groups, lr=1e-3)
         costs = []
-        for _ in range(iters):
-            pose = exp_se3(delta) @ T
-            res = port.cost_single(src, trg, k, pose, cfg, None if affine is None else (aff_s, aff_t))
-            loss = torch.mean(res['residual'])
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            opt.step()
-            costs.append(float(loss.detach()))
-            with torch.no_grad():
-                T = exp_se3(delta.detach()) @ T
-                delta.zero_()
+        for src_l, trg_l, n in zip(src, trg, iters):
+            for _ in range(n):
+                pose = exp_se3(delta) @ T
+                res = port.cost_single(src_l, trg_l, k, pose, cfg, None if affine is None else (aff_s, aff_t))
+                loss = torch.mean(res['residual'])
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                costs.append(float(loss.detach()))
+                with torch.no_grad():
+                    T = exp_se3(delta.detach()) @ T
+                    delta.zero_()
         return {'pose': T.detach(), 'k': k.detach(), 'aff_trg': None if aff_t is None else aff_t.detach(),
                 'costs': costs}
     finally:

@@ -901,17 +901,25 @@ static int sm_count() {
 }
 
 static inline int ctas_for(int n_tiles, int n_pairs, int occ) {
-    // every warp streams a strided set of tiles through its own ring.  Size the grid to a whole number of waves
-    // of the kernel's occupancy (`occ` CTAs/SM): ~4 waves over all pairs, rounded DOWN so the last wave is nearly
-    // full (a 5.3-wave grid wastes a third of its last wave).
+    // every warp streams a strided set of tiles through its own ring.  Size the grid to (nearly) a whole number of
+    // waves of the kernel's occupancy (`occ` CTAs/SM): the smallest CTA count per pair that gives >= 3 waves over all
+    // pairs with a last wave >= 97 % full, else the fullest within 8 waves (a 5.3-wave grid wastes a third of its last wave; 1024 pairs
+    // with one CTA each would run 2.3 waves at 77 %).
     const int max_ctas = (n_tiles + SPB_WARPS - 1) / SPB_WARPS;
     const int slots = sm_count() * occ;
     if (n_pairs < 1) n_pairs = 1;
     if ((long long)n_pairs * max_ctas <= slots) return max_ctas;
-    int want = (slots * 4) / n_pairs;
-    if (want > max_ctas) want = max_ctas;
-    if (want < 1) want = 1;
-    return want;
+    int best = 1;
+    double best_score = -1.0;
+    for (int c = 1; c <= max_ctas; ++c) {
+        const double w = (double)n_pairs * c / slots;
+        if (w > 8.0 && best_score >= 0.0) break;
+        const double eff = w / (double)(long long)(w + 0.999999);
+        if (w >= 3.0 && eff >= 0.97) return c;                       // the smallest grid that is good enough
+        const double score = (w >= 3.0 ? 1.0 : w / 3.0) * eff;       // fewer than 3 waves: the tail weighs more
+        if (score > best_score + 1e-9) { best_score = score; best = c; }
+    }
+    return best;
 }
 static inline int ctas_grad(int n_tiles, int n_pairs) { return ctas_for(n_tiles, n_pairs, Occ<MODE_GRAD, 6>::CTAS); }
 static inline int ctas_gn(int n_tiles, int n_pairs, int with_affine) {

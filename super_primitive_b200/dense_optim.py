@@ -29,6 +29,59 @@ from .geometry import CompactGeometry, _f32c, _stream, geometry_of, pack_rgba
 from .ops import project_points, transform_points  # noqa: F401  (re-exported like the reference)
 
 CHECK_FINITE_DEFAULT = True
+# The reference asserts finiteness at five sites per call, each a device->host sync (core/dense_optim.py:44,78,311,321,
+# 340-343).  Here the finalize kernel folds them into ONE device-side flag per pair; the flags of consecutive calls
+# land in a small ring on the device and the host looks at the ring once every CHECK_FINITE_EVERY calls (SURVEY 8(b):
+# "a replacement may defer to a device-side flag checked once per call (or per N calls) but should still raise
+# AssertionError").  So a non-finite value raises AssertionError at most CHECK_FINITE_EVERY - 1 calls late and a cost
+# evaluation never waits for the device.  cost_config['check_finite_every'] = 1 restores a check per call;
+# `flush_checks()` forces one now.
+CHECK_FINITE_EVERY = 16
+_RING_ROWS = 64
+
+
+class _FlagRing:
+    """per-device ring of finiteness flags written by the kernels (1.0 = fine)"""
+    rings = {}
+
+    def __init__(self, device):
+        self.flags = torch.ones((_RING_ROWS, nat.MAX_INLINE_PAIRS), dtype=torch.float32, device=device)
+        self.row = 0
+        self.pending = 0
+        self.rows_used = 0                 # rows written since the last look (never let the ring wrap unread)
+
+    @classmethod
+    def of(cls, device):
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        ring = cls.rings.get(key)
+        if ring is None:
+            ring = cls.rings[key] = cls(device)
+        return ring
+
+    def next_row(self):
+        r = self.flags[self.row]
+        self.row = (self.row + 1) % _RING_ROWS
+        self.rows_used += 1
+        return r
+
+    def called(self, every):
+        self.pending += 1
+        if self.pending >= max(1, int(every)) or self.rows_used >= _RING_ROWS - nat.MAX_INLINE_PAIRS:
+            self.check()
+
+    def check(self):
+        self.pending = 0
+        self.rows_used = 0
+        if float(self.flags.min()) < 0.5:          # the one device->host read
+            self.flags.fill_(1.0)
+            raise AssertionError("non-finite photometric cost, gradient or input (log-depth / pose)")
+
+
+def flush_checks():
+    """Look at the deferred finiteness flags of every device now (raises AssertionError like the reference's asserts)."""
+    for ring in list(_FlagRing.rings.values()):
+        ring.check()
+
 
 
 # ------------------------------------------------------------------------------------------------
@@ -97,18 +150,19 @@ class LazyResult(dict):
 def _launch_pairs(geom: CompactGeometry, level, trg_rgba, trg_Ks, poses, k, aff_src, aff_trg, tau,
                   stats=None):
     """poses (B,4,4), trg_rgba (B,Hl,Wl,4), trg_Ks (B,3,3) or (3,3), aff_trg (B,2)|None.
-    Returns out_pair (B,16), out_gk (B,N), out_pose (B,4,4), out_flag (B,)."""
+    Returns out_pair (B,16), out_gk (B,N), out_pose (B,4,4) and the device's flag ring."""
     lib = nat.lib()
     src_rgb, pack = level
     B = poses.shape[0]
     dev = poses.device
     Hl, Wl = trg_rgba.shape[1], trg_rgba.shape[2]
-    # one allocation for all per-call outputs: [pair 16 | pose 16 | flag 1] per pair, then gk
-    buf = torch.empty(B * 33 + B * geom.N, dtype=torch.float32, device=dev)
+    # one allocation for all per-call outputs: [pair 16 | pose 16] per pair, then gk; the finiteness flags go to the
+    # device-side ring (one row per launch)
+    buf = torch.empty(B * 32 + B * geom.N, dtype=torch.float32, device=dev)
     out_pair = buf[:B * 16].view(B, 16)
     out_pose = buf[B * 16:B * 32].view(B, 4, 4)
-    out_flag = buf[B * 32:B * 33]
-    out_gk = buf[B * 33:].view(B, geom.N)
+    out_gk = buf[B * 32:].view(B, geom.N)
+    ring = _FlagRing.of(dev)
     done = 0
     while done < B:
         nb = min(nat.MAX_INLINE_PAIRS, B - done)
@@ -132,10 +186,10 @@ def _launch_pairs(geom: CompactGeometry, level, trg_rgba, trg_Ks, poses, k, aff_
         if stats is not None:
             st_ref = C.byref(stats(done, nb))
         nat.check(lib.spb_cost_grad(geom.cref, pairs, nb, work.data_ptr(), out_pair[done:].data_ptr(),
-                                    out_gk[done:].data_ptr(), out_pose[done:].data_ptr(), out_flag[done:].data_ptr(),
+                                    out_gk[done:].data_ptr(), out_pose[done:].data_ptr(), ring.next_row().data_ptr(),
                                     st_ref, _stream()), "spb_cost_grad")
         done += nb
-    return out_pair, out_gk, out_pose, out_flag
+    return out_pair, out_gk, out_pose, ring
 
 
 class _PairCost(torch.autograd.Function):
@@ -148,13 +202,11 @@ class _PairCost(torch.autograd.Function):
         B = poses_c.shape[0]
         a_s = None if aff_src is None else _f32c(aff_src).reshape(-1)
         a_t = None if aff_trg is None else _f32c(aff_trg).reshape(-1, 2).expand(B, 2).contiguous()
-        out_pair, out_gk, out_pose, out_flag = _launch_pairs(geom, level, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau)
+        out_pair, out_gk, out_pose, ring = _launch_pairs(geom, level, trg_rgba, trg_Ks, poses_c, k_c, a_s, a_t, tau)
         if check:
-            # the reference asserts finiteness at five sites per call (core/dense_optim.py:44,78,311,321,340-343);
-            # here the finalize kernel folds outputs AND inputs (log-depth seeds, pose) into one flag per pair and
-            # a single device->host read covers the call.  (A NaN seed would otherwise just invalidate its points.)
-            if float(out_flag if B == 1 else out_flag.min()) < 0.5:
-                raise AssertionError("non-finite photometric cost, gradient or input (log-depth / pose)")
+            # outputs AND inputs (log-depth seeds, pose) are folded into one flag per pair by the finalize kernel
+            # (a NaN seed would otherwise just invalidate its points); the host reads the flags every `check` calls
+            ring.called(check)
         ctx.save_for_backward(out_pair, out_gk, out_pose)
         ctx.shapes = (None if aff_src is None else aff_src.shape, None if aff_trg is None else aff_trg.shape,
                       poses.shape)
@@ -183,14 +235,73 @@ class _PairCost(torch.autograd.Function):
         return g_k, g_pose, g_as, g_at, None, None, None, None, None, None
 
 
+_MODES = ('colour', 'colour_norm', 'colour_norm_kappa')
+
+
 def _check_cfg(cost_config):
+    """mode: the reference's `calculate_residual` (core/dense_optim.py:228-261) returns the COLOUR residual in every
+    mode that has colour channels -- `residual_cosine` is initialised to 0.0 and never assigned -- so 'colour_norm' and
+    'colour_norm_kappa' are accepted and cost what 'colour' costs; like the reference they read `normal_loss` and
+    `normal_weight` from the config (KeyError when missing) and carry the extra image channels through the statistics
+    (normals rotated by the detached R, core/normal_cost.py:11-30).  'norm_kappa' has no colour term: the reference's
+    residual is then the Python float 0.0, which none of its callers can back-propagate -- rejected here."""
     mode = cost_config['mode']
+    if mode not in _MODES:
+        if mode == 'norm_kappa':
+            raise NotImplementedError("residual mode 'norm_kappa': the reference evaluates it to the constant 0.0 "
+                                      "(no colour term, the normal term is never computed)")
+        raise ValueError(f"unknown residual mode {mode!r}")
     if mode != 'colour':
-        # the reference's normal/kappa terms are dead code (residual_cosine is never assigned,
-        # core/dense_optim.py:241-261) and every caller forces 'colour'
-        raise NotImplementedError(f"residual mode {mode!r}: only 'colour' is implemented "
-                                  "(the reference never computes the normal term)")
-    return cost_config['collect_stats'], cost_config.get('check_finite', CHECK_FINITE_DEFAULT)
+        cost_config['normal_loss'], cost_config['normal_weight']      # noqa: B018  (the reference's KeyError)
+    check = cost_config.get('check_finite', CHECK_FINITE_DEFAULT)
+    every = int(cost_config.get('check_finite_every', CHECK_FINITE_EVERY)) if check else 0
+    return cost_config['collect_stats'], every
+
+
+def _mode_channels(mode, C):
+    """channel count the reference's `split_by_mode` insists on (torch.split raises otherwise)"""
+    need = {'colour': None, 'colour_norm': 6, 'colour_norm_kappa': 7}[mode]
+    if need is not None and C != need:
+        raise AssertionError(f"residual mode {mode!r} needs {need} image channels, got {C}")
+
+
+def _sample_extra(extra, xn, yn):
+    """bilinear samples (zeros padding, align_corners) of the non-colour channels `extra` (B,C',Hl,Wl) at normalised
+    coordinates xn, yn (B,P) -> (B,C',P).  Statistics path only (visualisation): plain torch, like the reference."""
+    grid = torch.stack([xn, yn], -1)[:, None]                       # (B,1,P,2)
+    out = torch.nn.functional.grid_sample(extra, grid, mode='bilinear', padding_mode='zeros', align_corners=True)
+    return out[:, :, 0, :]
+
+
+def _extra_channel_stats(out, geom, src_image, trg_images, trg_Ks, poses_c, mode):
+    """Images with more than three channels (normals, kappa; frontend `include_normals`): the reference's per-point
+    statistics carry every channel (core/dense_optim.py:315-325,347-350) and, outside 'colour' mode, rotate the source
+    normals into the target frame with the detached R (core/normal_cost.py:11-30).  The residual never uses them."""
+    B = poses_c.shape[0]
+    dev = poses_c.device
+    H, W = geom.H, geom.W
+    uv = geom.uv[geom.pad_index()]
+    u = (uv & 0xffff).to(torch.float32)
+    v = ((uv >> 16) & 0x7fff).to(torch.float32)
+    inv = 1.0 / (torch.tensor([W, H], dtype=torch.float32, device=dev) - 1)      # tool/point_utils.py:31-35
+    src_extra = _sample_extra(src_image[None, 3:].float(), (2 * u * inv[0] - 1)[None], (2 * v * inv[1] - 1)[None])
+    src_px = out['src_pixels']
+    if mode == 'colour':
+        out['src_pixels'] = torch.cat([src_px, src_extra], 1)
+    else:
+        R = poses_c[:, :3, :3]
+        normals = torch.einsum('bij,jn->bin', R, src_extra[0, :3])
+        parts = [src_px.expand(B, -1, -1), normals]
+        if src_extra.shape[1] > 3:
+            parts.append(src_extra[:, 3:].expand(B, -1, -1))
+        out['src_pixels'] = torch.cat(parts, 1)
+    moved = out['src_in_trg_pts'] if out['src_in_trg_pts'].dim() == 3 else out['src_in_trg_pts'][None]
+    proj = _project(moved, trg_Ks if trg_Ks.dim() == 3 else trg_Ks[None])
+    norm = 2 * proj * inv - 1
+    timg = trg_images if trg_images.dim() == 4 else trg_images[None]
+    trg_extra = _sample_extra(timg[:, 3:].float(), norm[..., 0], norm[..., 1])
+    out['src_in_trg_pixels'] = torch.cat([out['src_in_trg_pixels'], trg_extra], 1)
+    return out
 
 
 def _affine_pair(affine_comp):
@@ -278,6 +389,7 @@ def photomeric_cost(src_keyframe, trg_keyframe, src_keypoint_logdepth, pose, cos
     """Masked L1 photometric cost of the source segments warped into one target frame.
     Returns ``{'residual': (1,)}`` (+ statistics when ``collect_stats > 0``)."""
     collect_stats, check = _check_cfg(cost_config)
+    _mode_channels(cost_config['mode'], src_keyframe.image.shape[0])
     geom = geometry_of(src_keyframe)
     level = geom.level_buffers(src_keyframe.image)
     trg_rgba = pack_rgba(trg_keyframe.image)
@@ -294,11 +406,13 @@ def photomeric_cost(src_keyframe, trg_keyframe, src_keypoint_logdepth, pose, cos
     as_c = None if a_s is None else _f32c(a_s).reshape(-1).clone()
     at_c = None if a_t is None else _f32c(a_t).reshape(1, 2).clone()
     K_img = _f32c(trg_keyframe.K_img)
-    src_image = src_keyframe.image
+    src_image, trg_image, mode = src_keyframe.image, trg_keyframe.image, cost_config['mode']
 
     def produce():
         with torch.no_grad():
             out = _point_stats(geom, src_image, level, trg_rgba, trg_K, poses_c, k_c, as_c, at_c, tau, False)
+            if src_image.shape[0] > 3:
+                out = _extra_channel_stats(out, geom, src_image, trg_image, trg_K, poses_c, mode)
             if collect_stats > 1:
                 out.update(_keypoint_stats(geom, k_c, poses_c, trg_K, K_img, tau, False))
         return out
@@ -355,13 +469,58 @@ def unproject_kf(kf, keypoint_logdepth, jacobian=False):
     src_ok = torch.empty(P, dtype=torch.uint8, device=dev)
     nat.check(nat.lib().spb_lift_points(geom.cref, k_c.data_ptr(), src_pts.data_ptr(), seg_ids.data_ptr(),
                                         src_ok.data_ptr(), _stream()), "spb_lift_points")
-    src_rgb = geom.source_samples(kf.image)
-    src_pixels = src_rgb[:, geom.pad_index()][None].contiguous()
-    return {'src_pixels': src_pixels,
-            'src_valid_mask': src_ok.bool()[None],
-            'src_pts': src_pts,
-            'segm_ids': seg_ids,
-            'spatial_size': kf.geo_spatial_dim()}
+    level = geom.level_buffers(kf.image)
+    src_pixels = level[0][:, geom.pad_index()][None].contiguous()
+    if kf.image.shape[0] > 3:
+        # every channel of the keyframe image, like the reference's get_pixels (core/dense_optim.py:190-192)
+        src_pixels = _extra_channel_stats({'src_pixels': src_pixels, 'src_in_trg_pts': src_pts,
+                                           'src_in_trg_pixels': src_pixels}, geom, kf.image, kf.image, geom.K.reshape(3, 3),
+                                          torch.eye(4, device=dev)[None], 'colour')['src_pixels'].contiguous()
+    out = _Precomputed({'src_pixels': src_pixels,
+                        'src_valid_mask': src_ok.bool()[None],
+                        'src_pts': src_pts,
+                        'segm_ids': seg_ids,
+                        'spatial_size': kf.geo_spatial_dim()})
+    # what `photomeric_cost_precomputed` needs to serve this dict with the fused compact-geometry kernel (the tile-major
+    # stream of the same points) instead of the generic point-list kernel; dropped as soon as a caller edits the dict
+    out._spb = (geom, level, k_c.clone(), src_pts, src_pixels)
+    return out
+
+
+class _Precomputed(dict):
+    """The dict `unproject_kf` returns (core/dense_optim.py:176-200), plus a private handle on the compact geometry it
+    was lifted from.  Any mutation of the dict invalidates the handle (the generic kernel then serves it)."""
+    _spb = None
+
+    def _drop(self):
+        self._spb = None
+
+    def __reduce__(self):                       # pickles / deep-copies as the plain dict the reference returns
+        return (dict, (dict(self),))
+
+    def __setitem__(self, key, value):
+        self._drop()
+        super().__setitem__(key, value)
+
+    def __delitem__(self, key):
+        self._drop()
+        super().__delitem__(key)
+
+    def update(self, *a, **kw):
+        self._drop()
+        super().update(*a, **kw)
+
+    def pop(self, *a):
+        self._drop()
+        return super().pop(*a)
+
+    def clear(self):
+        self._drop()
+        super().clear()
+
+    def setdefault(self, *a):
+        self._drop()
+        return super().setdefault(*a)
 
 
 class _PointsCost(torch.autograd.Function):
@@ -380,8 +539,11 @@ class _PointsCost(torch.autograd.Function):
         nat.check(lib.spb_cost_grad_points(src_pts.data_ptr(), src_px.data_ptr(), src_ok.data_ptr(), P,
                                            int(dims[0]), int(dims[1]), C.byref(pr), work.data_ptr(),
                                            out_pair.data_ptr(), _stream()), "spb_cost_grad_points")
-        if check and not bool(torch.isfinite(out_pair).all() & torch.isfinite(pose_c).all()):
-            raise AssertionError("non-finite photometric cost, gradient or pose")
+        if check:
+            ring = _FlagRing.of(dev)
+            ring.next_row().copy_((torch.isfinite(out_pair).all() & torch.isfinite(pose_c).all()).to(torch.float32)
+                                  .expand(nat.MAX_INLINE_PAIRS))
+            ring.called(check)
         ctx.save_for_backward(out_pair)
         ctx.shapes = (None if aff_src is None else aff_src.shape, None if aff_trg is None else aff_trg.shape)
         return out_pair[0:1].clone()
@@ -407,8 +569,20 @@ class _PointsCost(torch.autograd.Function):
 
 def photomeric_cost_precomputed(src_precomputed, trg_keyframe, pose, cost_config, affine_comp=None):
     """Tracking cost against pre-lifted source points (core/dense_optim.py:365-403): only the pose
-    and the affine terms receive gradients."""
+    and the affine terms receive gradients.
+
+    A dict that came from this package's `unproject_kf` (and was not edited since) is served by the fused
+    compact-geometry kernel -- the same points, streamed tile-major with one bulk copy per tile -- at the seeds the
+    points were lifted with; any other dict goes through the generic point-list kernel (`spb_cost_grad_points`)."""
     _, check = _check_cfg(cost_config)
+    a_s, a_t = _affine_pair(affine_comp)
+    trg_rgba = pack_rgba(trg_keyframe.image)
+    handle = getattr(src_precomputed, "_spb", None)
+    if handle is not None and handle[3] is src_precomputed['src_pts'] and handle[4] is src_precomputed['src_pixels'] \
+            and handle[3]._version == 0 and handle[4]._version == 0:
+        geom, level, k_c = handle[:3]
+        residual = _PairCost.apply(k_c, pose[None], a_s, a_t, geom, level, trg_rgba, _f32c(trg_keyframe.K), 1e-7, check)
+        return {'residual': residual}
     src_pts = _f32c(src_precomputed['src_pts'])
     P = src_pts.shape[0]
     src_px = _f32c(src_precomputed['src_pixels'])[0, :3].contiguous()
@@ -416,8 +590,6 @@ def photomeric_cost_precomputed(src_precomputed, trg_keyframe, pose, cost_config
     src_ok = (src_ok if src_ok.dtype == torch.bool else src_ok != 0).contiguous().view(torch.uint8)
     if src_px.shape[1] != P or src_ok.shape[0] != P:
         raise AssertionError("src_precomputed tensors disagree on the number of points")
-    a_s, a_t = _affine_pair(affine_comp)
-    trg_rgba = pack_rgba(trg_keyframe.image)
     residual = _PointsCost.apply(pose, a_s, a_t, src_pts, src_px, src_ok, tuple(src_precomputed['spatial_size']),
                                  trg_rgba[0], _f32c(trg_keyframe.K), check)
     return {'residual': residual}

@@ -43,8 +43,11 @@ class FrameIngest:
     (`host_arena`) that a loader decodes into -- so a chunk of pairs is ONE host->device copy (`upload`) followed by
     the three launches of `spb_ingest_u8` (`run`)."""
 
-    def __init__(self, problems, geoms, lean=False):
-        """``lean``: do not materialise the planar float source frame and the [3][n_pad] sample array (only the
+    def __init__(self, problems, geoms, lean=False, target_only=False):
+        """``target_only``: only the TARGET frame of every pair arrives (the odometry case: the source keyframe and
+        everything derived from it stay resident, a new camera frame is aligned against it; odometery/odometery.py:323-403);
+        the staging buffer then holds one frame per problem and the source half of the ingest is skipped.
+        ``lean``: do not materialise the planar float source frame and the [3][n_pad] sample array (only the
         statistics path reads them).  Needs a library built with the fused source ingest (experiment switch,
         ``spb_version() // 1000 & 1``); the default library derives the tile pack from those two buffers."""
         import ctypes as C
@@ -55,8 +58,10 @@ class FrameIngest:
         self.n = len(problems)
         sizes = [3 * int(p['trg_rgba'].shape[0]) * int(p['trg_rgba'].shape[1]) for p in problems]
         self.offsets = [0]
+        self.target_only = bool(target_only)
+        per = 1 if target_only else 2
         for b in sizes:
-            self.offsets.append(self.offsets[-1] + 2 * ((b + 15) // 16 * 16))      # 16-byte aligned frames
+            self.offsets.append(self.offsets[-1] + per * ((b + 15) // 16 * 16))      # 16-byte aligned frames
         self.stage = torch.empty(self.offsets[-1], dtype=torch.uint8, device=dev)
         self.src_planar = []
         jarr = (nat.SpbFrameJob * self.n)()
@@ -65,16 +70,18 @@ class FrameIngest:
         for i, p in enumerate(problems):
             Hl, Wl = int(p['trg_rgba'].shape[0]), int(p['trg_rgba'].shape[1])
             g = p['geom']
-            half = (self.offsets[i + 1] - self.offsets[i]) // 2
-            so, to = self.offsets[i], self.offsets[i] + half
+            half = (self.offsets[i + 1] - self.offsets[i]) // per
+            so, to = self.offsets[i], self.offsets[i] + (0 if target_only else half)
             self._views.append((so, to, Hl, Wl))
-            pl = torch.empty((3, Hl, Wl), dtype=torch.float32, device=dev)
+            pl = None if (lean or target_only) else torch.empty((3, Hl, Wl), dtype=torch.float32, device=dev)
             self.src_planar.append(pl)
             j = jarr[i]
-            j.src_u8, j.trg_u8 = self.stage.data_ptr() + so, self.stage.data_ptr() + to
-            j.src_planar = None if lean else pl.data_ptr()
-            j.src_rgb = None if lean else p['src_rgb'].data_ptr()
-            j.pack, j.trg_rgba = p['pack'].data_ptr(), p['trg_rgba'].data_ptr()
+            j.src_u8 = None if target_only else self.stage.data_ptr() + so
+            j.trg_u8 = self.stage.data_ptr() + to
+            j.src_planar = None if pl is None else pl.data_ptr()
+            j.src_rgb = None if (lean or target_only) else p['src_rgb'].data_ptr()
+            j.pack = None if target_only else p['pack'].data_ptr()
+            j.trg_rgba = p['trg_rgba'].data_ptr()
             j.geom, j.Hl, j.Wl = gidx[id(g)], Hl, Wl
             self.max_pixels = max(self.max_pixels, Hl * Wl)
             self.max_pad = max(self.max_pad, g.P_pad)
@@ -90,13 +97,14 @@ class FrameIngest:
         """Write the (Hl,Wl,3) uint8 frames of problem ``i`` into ``arena`` (what a loader does when it decodes)."""
         so, to, Hl, Wl = self._views[i]
         n = 3 * Hl * Wl
-        arena[so:so + n].copy_(src_u8.reshape(-1))
+        if not self.target_only:
+            arena[so:so + n].copy_(src_u8.reshape(-1))
         arena[to:to + n].copy_(trg_u8.reshape(-1))
 
     def frame_bytes(self, first=0, count=None):
         """payload bytes (without alignment padding) of the frames of problems [first, first + count)"""
         count = self.n - first if count is None else count
-        return sum(2 * 3 * v[2] * v[3] for v in self._views[first:first + count])
+        return sum((1 if self.target_only else 2) * 3 * v[2] * v[3] for v in self._views[first:first + count])
 
     def upload(self, arena, first=0, count=None):
         """ONE asynchronous host->device copy of the frames of problems [first, first + count) on the current stream."""

@@ -42,6 +42,10 @@ class AlignmentBatch:
         k         (N,) initial log-depth seeds
         aff_src, aff_trg   optional (2,) tensors
         tau       optional front-of-camera threshold (default 1e-7)
+        levels    optional list, COARSE -> FINE, of dict(src_rgb, pack, trg_rgba): the image pyramid of the pair
+                  (geometry, pose, seeds and brightness terms are shared by the levels, as keyframe_pyramid(geo_down=False)
+                  shares them, image/keyframe.py:125-146).  Without it the problem has the one level given by the
+                  top-level src_rgb / pack / trg_rgba.  Every problem of a batch must have the same number of levels.
     """
 
     def __init__(self, problems, with_affine=False, irls_eps=1e-3, lam0=1e-3, hold_depth=False):
@@ -84,29 +88,44 @@ class AlignmentBatch:
                                     for p in problems]).contiguous()
         self.aff_trg = torch.stack([_f32c(p.get('aff_trg', zero2) if p.get('aff_trg') is not None else zero2)
                                     for p in problems]).contiguous()
-        self._keep = [(p['src_rgb'], p['trg_rgba'], p['pack']) for p in problems]
+        def lv_of(p):
+            lv = p.get('levels')
+            return list(lv) if lv else [dict(src_rgb=p['src_rgb'], pack=p['pack'], trg_rgba=p['trg_rgba'])]
+
+        plv = [lv_of(p) for p in problems]
+        self.n_levels = len(plv[0])
+        if any(len(lv) != self.n_levels for lv in plv):
+            raise ValueError("every problem of a batch needs the same number of pyramid levels")
+        self._keep_lv = [[(lv[l]['src_rgb'], lv[l]['trg_rgba'], lv[l]['pack']) for lv in plv]
+                         for l in range(self.n_levels)]
         use_aff = self.with_affine or any(p.get('aff_src') is not None for p in problems)
         self.use_affine = use_aff
-        # descriptor arrays
+        # descriptor arrays: one SpbPair array per pyramid level (only the image-derived pointers differ)
         garr = (nat.SpbGeom * len(geoms))()
         for i, g in enumerate(geoms):
             garr[i] = g.c
-        parr = (nat.SpbPair * n)()
-        for i, p in enumerate(problems):
-            q = parr[i]
-            q.trg_rgba = p['trg_rgba'].data_ptr()
-            q.src_rgb = p['src_rgb'].data_ptr()
-            q.tile_pack = p['pack'].data_ptr()
-            q.K_trg = self.K_trg[i].data_ptr()
-            q.pose = self.poses[i].data_ptr()
-            q.k = self.k.data_ptr() + 4 * int(seg_off[i])
-            q.aff_src = self.aff_src[i].data_ptr() if use_aff else None
-            q.aff_trg = self.aff_trg[i].data_ptr() if use_aff else None
-            q.geom = gidx[i]
-            q.Hl, q.Wl = p['trg_rgba'].shape[0], p['trg_rgba'].shape[1]
-            q.tau = float(p.get('tau', 1e-7))
+        self.d_pairs_lv = []
+        for l in range(self.n_levels):
+            parr = (nat.SpbPair * n)()
+            for i, p in enumerate(problems):
+                src_rgb, trg_rgba, pack = self._keep_lv[l][i]
+                q = parr[i]
+                q.trg_rgba = trg_rgba.data_ptr()
+                q.src_rgb = src_rgb.data_ptr()
+                q.tile_pack = pack.data_ptr()
+                q.K_trg = self.K_trg[i].data_ptr()
+                q.pose = self.poses[i].data_ptr()
+                q.k = self.k.data_ptr() + 4 * int(seg_off[i])
+                q.aff_src = self.aff_src[i].data_ptr() if use_aff else None
+                q.aff_trg = self.aff_trg[i].data_ptr() if use_aff else None
+                q.geom = gidx[i]
+                q.Hl, q.Wl = trg_rgba.shape[0], trg_rgba.shape[1]
+                q.tau = float(p.get('tau', 1e-7))
+            self.d_pairs_lv.append(_struct_array_to_device(parr, dev))
+        self.level = self.n_levels - 1                       # finest
+        self.d_pairs = self.d_pairs_lv[self.level]
+        self._keep = self._keep_lv[self.level]
         self.d_geoms = _struct_array_to_device(garr, dev)
-        self.d_pairs = _struct_array_to_device(parr, dev)
         self.d_seg_off = torch.from_numpy(seg_off).to(dev)
         self.d_seg_cnt = torch.from_numpy(seg_cnt).to(dev)
         # workspaces / outputs
@@ -209,43 +228,91 @@ class AlignmentBatch:
                                             _stream()), "spb_adam_update")
         self.launches += 1
 
-    def run_adam(self, iters, **kw):
-        for _ in range(iters):
-            self.adam_step(**kw)
+    # ---- coarse-to-fine schedule ------------------------------------------------------------------
+    def set_level(self, level):
+        """Select the pyramid level the next iterations run on (0 = coarsest).  Poses, seeds, brightness terms and
+        the optimiser state carry over; the LM acceptance baseline is re-armed because the cost of another level is
+        not comparable (the damping factor is kept)."""
+        if not 0 <= level < self.n_levels:
+            raise ValueError(f"level {level} outside 0..{self.n_levels - 1}")
+        if level != self.level:
+            self.level = level
+            self.d_pairs = self.d_pairs_lv[level]
+            self._keep = self._keep_lv[level]
+            self.lm_state[:, 2] = 0.0
 
-    def capture_adam(self, iters, **kw):
-        """CUDA-graph ``iters`` first-order iterations. Returns the graph."""
+    def _schedule(self, iters):
+        """iters: int (all on the current level) or a per-level sequence, coarse -> fine, the reference's
+        `for pyr_level ... for i in range(steps)` (odometery/two_frame_sfm.py:150-155, odometery/odometery.py:376-384)."""
+        if isinstance(iters, int):
+            return [(self.level, iters)]
+        iters = list(iters)
+        if len(iters) != self.n_levels:
+            raise ValueError(f"{len(iters)} iteration counts for {self.n_levels} pyramid levels")
+        return [(l, int(n)) for l, n in enumerate(iters) if int(n) > 0]
+
+    def run_adam(self, iters, **kw):
+        for level, n in self._schedule(iters):
+            self.set_level(level)
+            for _ in range(n):
+                self.adam_step(**kw)
+
+    def _capture(self, step, iters, kw):
+        sched = self._schedule(iters)
+        saved = self._snapshot()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self.adam_step(**kw)    # warm-up outside capture
+            for level, _ in sched:                     # warm-up outside capture (module load, lazy allocations) ...
+                self.set_level(level)
+                step(**kw)
         torch.cuda.current_stream().wait_stream(s)
+        self._restore(saved)                           # ... which must not count as an iteration
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            for _ in range(iters):
-                self.adam_step(**kw)
+            for level, n in sched:
+                self.set_level(level)
+                for _ in range(n):
+                    step(**kw)
         return graph
+
+    def _state_tensors(self):
+        ts = [self.poses, self.k, self.aff_trg, self.lm_state, self.saved_pair, self.saved_seg]
+        if getattr(self, "adam_pair", None) is not None:
+            ts += [self.adam_pair, self.adam_seg]
+        return ts
+
+    def _snapshot(self):
+        return (self.level, [t.clone() for t in self._state_tensors()])
+
+    def _restore(self, saved):
+        level, vals = saved
+        for t, v in zip(self._state_tensors(), vals):
+            t.copy_(v)
+        self.level = level
+        self.d_pairs = self.d_pairs_lv[level]
+        self._keep = self._keep_lv[level]
+
+    def capture_adam(self, iters, **kw):
+        """CUDA-graph `iters` first-order iterations (int, or per level coarse -> fine); replaying the graph applies
+        exactly those iterations (the warm-up step taken before capture is rolled back).  Returns the graph."""
+        self._adam_buffers()
+        return self._capture(self.adam_step, iters, kw)
 
     def grad_costs(self):
         """mean |r| per problem at the parameters of the last gradient evaluation (grad_step / adam_step)."""
         return self.out_pair[:, 0]
 
     def run_gn(self, iters):
-        for _ in range(iters):
-            self.gn_step()
+        for level, n in self._schedule(iters):
+            self.set_level(level)
+            for _ in range(n):
+                self.gn_step()
 
     def capture_gn(self, iters):
-        """CUDA-graph ``iters`` GN iterations (launch-bound small batches). Returns the graph."""
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            self.gn_step()          # warm-up outside capture
-        torch.cuda.current_stream().wait_stream(s)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            for _ in range(iters):
-                self.gn_step()
-        return graph
+        """CUDA-graph `iters` GN iterations (int, or per level coarse -> fine; launch-bound small batches); replaying
+        applies exactly those iterations.  Returns the graph."""
+        return self._capture(self.gn_step, iters, {})
 
     # ---- results -------------------------------------------------------------------------------
     def costs(self):
@@ -279,11 +346,23 @@ class AlignmentBatch:
         return total
 
 
-def make_problem(src_kf, trg_image, trg_K, pose, k, geom=None, aff_src=None, aff_trg=None, tau=1e-7):
-    """Convenience: build one problem dict from a source keyframe (dense) and a planar target image."""
+def make_problem(src_kf, trg_image, trg_K, pose, k, geom=None, aff_src=None, aff_trg=None, tau=1e-7, levels=None):
+    """Convenience: build one problem dict from a source keyframe (dense) and a planar target image.
+    levels = (start_level, end_level): additionally the image pyramid of both frames, `keyframe_pyramid`'s levels
+    (image/keyframe.py:77-148: 3x3 blur + decimation per level, geometry shared), coarse -> fine."""
     if geom is None:
         geom = CompactGeometry(src_kf.keypoint_regions, src_kf.get_logdepth(), src_kf.keypoints, src_kf.K)
-    src_rgb, pack = geom.level_buffers(src_kf.image)
-    trg_rgba = pack_rgba(trg_image)[0]
-    return dict(geom=geom, src_rgb=src_rgb, pack=pack, trg_rgba=trg_rgba, K_trg=trg_K, pose=pose, k=k,
-                aff_src=aff_src, aff_trg=aff_trg, tau=tau)
+    out = dict(geom=geom, K_trg=trg_K, pose=pose, k=k, aff_src=aff_src, aff_trg=aff_trg, tau=tau)
+    if levels is None:
+        src_rgb, pack = geom.level_buffers(src_kf.image)
+        out.update(src_rgb=src_rgb, pack=pack, trg_rgba=pack_rgba(trg_image)[0])
+        return out
+    from .pyramid import _levels, _pyr_down
+    start, end = levels
+    lv = []
+    for s_img, t_img in zip(_levels(_f32c(src_kf.image[:3]), start, end, _pyr_down),
+                            _levels(_f32c(trg_image[:3]), start, end, _pyr_down)):
+        src_rgb, pack = geom.level_buffers(s_img)
+        lv.append(dict(src_rgb=src_rgb, pack=pack, trg_rgba=pack_rgba(t_img)[0], src_image=s_img, trg_image=t_img))
+    out.update(levels=lv, src_rgb=lv[-1]['src_rgb'], pack=lv[-1]['pack'], trg_rgba=lv[-1]['trg_rgba'])
+    return out

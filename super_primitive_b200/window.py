@@ -175,12 +175,18 @@ class MappingWindows:
             self.step(**kw)
 
     def capture(self, iters, **kw):
-        """CUDA-graph ``iters`` iterations (after one eager warm-up step). Returns the graph."""
+        """CUDA-graph ``iters`` iterations; replaying the graph applies exactly those (the eager warm-up step taken
+        before capture -- module load, lazy allocations -- is rolled back).  Returns the graph."""
+        state = [t for t in (self.frame_T, self.frame_aff, self.k, self.edge_pose, self.adam_frame, self.adam_seg,
+                             self.win_state) if t is not None]
+        saved = [t.clone() for t in state]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             self.step(**kw)
         torch.cuda.current_stream().wait_stream(s)
+        for t, v in zip(state, saved):
+            t.copy_(v)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             for _ in range(iters):

@@ -80,7 +80,7 @@ def test_fused_iteration_equals_gradient_then_update_and_graph_replay():
         a.adam_step()
         b.grad_step()
         b.adam_update()
-    graph = c.capture_adam(5)           # one eager warm-up step + 5 captured
+    graph = c.capture_adam(6)           # the warm-up step before capture is rolled back: replay = 6 iterations
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(a.poses, b.poses) and torch.equal(a.k, b.k)
@@ -103,3 +103,46 @@ def test_adam_reduces_cost_of_a_consistent_scene():
     batch.grad_step()
     c1 = float(batch.grad_costs()[0])
     assert c1 < 0.5 * c0, f"cost {c0} -> {c1}"
+
+
+def test_coarse_to_fine_schedule_matches_the_oracle_and_graph_replay():
+    """`AlignmentBatch.run_adam([n0, n1, n2])` walks the image pyramid coarse -> fine with one optimiser state, like the
+    reference's `for pyr_level ... for iter in range(steps[pyr_level])` (odometery/odometery.py:376-384,
+    odometery/two_frame_sfm.py:150-155); geometry, pose and seeds are shared by the levels."""
+    from oracle import adam_loop
+    from super_primitive_b200 import synthetic as syn
+    from super_primitive_b200.solver import AlignmentBatch, make_problem
+    iters = [5, 4, 6]
+    src, trg, k0, pose0 = _problem(11, H=96, W=128, N=8, kind="overlap")
+    sl, tl = syn.keyframe_pyramid(src, 0, 3), syn.keyframe_pyramid(trg, 0, 3)
+    w64 = adam_loop.tracker_adam([_f64(s) for s in sl], [_f64(t) for t in tl], k0.double(), pose0.double(), iters)
+    w32 = adam_loop.tracker_adam(sl, tl, k0, pose0, iters)
+
+    def build():
+        return AlignmentBatch([make_problem(src.to("cuda"), trg.to("cuda").image, trg.K.cuda(), pose0.cuda(), k0.cuda(),
+                                            levels=(0, 3))])
+
+    a = build()
+    assert a.n_levels == 3 and a.level == 2
+    costs = []
+    for level, n in enumerate(iters):
+        a.set_level(level)
+        for _ in range(n):
+            a.adam_step()
+            costs.append(float(a.grad_costs()[0]))
+    for name, got in (("pose", to_np(a.poses_matrix()[0])), ("k", to_np(a.k_of(0)))):
+        e_gpu, e_ref = _err(got, to_np(w64[name])), _err(to_np(w32[name]), to_np(w64[name]))
+        assert e_gpu <= max(1e-4, 2.0 * e_ref), f"{name}: GPU {e_gpu:.2e}, float32 oracle {e_ref:.2e}"
+    assert_close(np.asarray(costs), np.asarray(w64["costs"]), 1e-4, "cost trajectory over the three levels")
+    b, c = build(), build()
+    b.run_adam(iters)
+    graph = c.capture_adam(iters)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(a.poses, b.poses) and torch.equal(a.k, b.k)
+    assert torch.equal(a.poses, c.poses) and torch.equal(a.k, c.k)
+    # the GN/LM loop accepts the same schedule and re-arms its acceptance test at every level switch
+    d = build()
+    d.run_gn([3, 3, 3])
+    torch.cuda.synchronize()
+    assert float(d.lm_state[0, 3]) >= 3 and np.all(np.isfinite(to_np(d.poses)))

@@ -124,10 +124,20 @@ def test_full_size_consistency_properties(H, W, N):
     P = pre['src_pts'].shape[0]
     assert P == int(src.keypoint_regions.sum())
     pose = _leaf(pose0)
-    out2 = do.photomeric_cost_precomputed(pre, trg, pose, CFG0)
+    out2 = do.photomeric_cost_precomputed(dict(pre), trg, pose, CFG0)      # a plain dict: the generic point-list kernel
     out2['residual'].mean().backward()
     assert_close(to_np(out2['residual']), to_np(res), 2e-5, "compact vs points kernel: cost")
     assert_close(to_np(pose.grad), to_np(gp), 2e-4, "compact vs points kernel: pose gradient")
+    # the dict as unproject_kf returned it is served by the fused compact kernel at the lifted seeds: same launch
+    # as photomeric_cost => bit-identical
+    pose3 = _leaf(pose0)
+    out3 = do.photomeric_cost_precomputed(pre, trg, pose3, CFG0)
+    out3['residual'].mean().backward()
+    assert torch.equal(out3['residual'], res) and torch.equal(pose3.grad, gp)
+    pre['src_pts'] = pre['src_pts'] * 1.0                                  # an edited dict falls back to the generic kernel
+    assert getattr(pre, "_spb", None) is None
+    out4 = do.photomeric_cost_precomputed(pre, trg, _leaf(pose0), CFG0)
+    assert_close(to_np(out4['residual']), to_np(res), 2e-5, "edited dict: generic kernel")
 
 
 def test_full_size_gn_converges_c2():

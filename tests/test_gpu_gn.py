@@ -120,7 +120,7 @@ def test_graph_replay_equals_eager():
     a = build()
     a.run_gn(6)
     b = build()
-    graph = b.capture_gn(5)          # capture_gn runs one eager warm-up step first
+    graph = b.capture_gn(6)          # the warm-up step before capture is rolled back: replay = 6 iterations
     graph.replay()
     torch.cuda.synchronize()
     assert_close(to_np(b.poses), to_np(a.poses), 1e-6, "graph vs eager poses")

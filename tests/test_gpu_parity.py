@@ -249,7 +249,16 @@ def test_non_finite_inputs_raise_assertion():
     k = g.k()
     k[0] = float("nan")
     with pytest.raises(AssertionError):
-        do.photomeric_cost(g.src(0), g.trg(0), k, g.poses()[0], CFG0)
+        do.photomeric_cost(g.src(0), g.trg(0), k, g.poses()[0], dict(CFG0, check_finite_every=1))
+    # default: the device-side flags are read every CHECK_FINITE_EVERY calls (no host sync per evaluation), so the
+    # AssertionError arrives within that many calls -- or at once with flush_checks()
+    do.photomeric_cost(g.src(0), g.trg(0), k, g.poses()[0], CFG0)
+    with pytest.raises(AssertionError):
+        do.flush_checks()
+    do.flush_checks()                                           # the ring is clean again
+    with pytest.raises(AssertionError):
+        for _ in range(do.CHECK_FINITE_EVERY + 1):
+            do.photomeric_cost(g.src(0), g.trg(0), k, g.poses()[0], CFG0)
     with pytest.raises(AssertionError):
         do.unproject_kf(g.src(0), k)
 

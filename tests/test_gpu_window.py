@@ -146,7 +146,7 @@ def test_graph_replay_and_early_stop():
 
     a, b = build(), build()
     a.run(7, **LRS)
-    graph = b.capture(6, **LRS)               # one eager warm-up step + 6 captured
+    graph = b.capture(7, **LRS)               # the warm-up step before capture is rolled back: replay = 7 iterations
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(a.frame_T, b.frame_T) and torch.equal(a.k, b.k)

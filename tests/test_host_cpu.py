@@ -128,8 +128,18 @@ def test_cpu_tensors_are_refused():
     src, trg, k0, pose0 = syn.two_frame_problem(16, 24, 2)
     with pytest.raises(RuntimeError):
         do.photomeric_cost(src, trg, k0, pose0, {'mode': 'colour', 'collect_stats': 0})
-    with pytest.raises(NotImplementedError):
+    # mode handling mirrors the reference (core/cost_utils.py:4-19, core/dense_optim.py:228-236): outside 'colour' the
+    # config must carry normal_loss / normal_weight (KeyError), the image must have the mode's channel count, and
+    # 'norm_kappa' (no colour term: the reference's residual is the constant 0.0) is rejected
+    with pytest.raises(KeyError):
         do.photomeric_cost(src, trg, k0, pose0, {'mode': 'colour_norm', 'collect_stats': 0})
+    full = {'collect_stats': 0, 'normal_loss': 'lecrec', 'normal_weight': 0.1}
+    with pytest.raises(AssertionError):
+        do.photomeric_cost(src, trg, k0, pose0, dict(full, mode='colour_norm'))          # 3 channels, 6 needed
+    with pytest.raises(NotImplementedError):
+        do.photomeric_cost(src, trg, k0, pose0, dict(full, mode='norm_kappa'))
+    with pytest.raises(ValueError):
+        do.photomeric_cost(src, trg, k0, pose0, dict(full, mode='depth'))
 
 
 def test_lazy_result_materialises_once():
