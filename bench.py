@@ -227,6 +227,14 @@ class HostStaged:
         self.d2h = (self.o_pose.numel() + self.o_k.numel() + self.o_cost.numel()) * 4
         self.copy_stream = torch.cuda.Stream()
         self.events = [torch.cuda.Event() for _ in problems]
+        # pose + seeds travel FIRST on the copy stream into their own double-buffered staging and are moved into place on
+        # the compute stream: issued on the compute stream they would queue in the H2D engine behind the NEXT step's
+        # frame copies (the host runs ahead) and hold the iteration back by a whole step (round 1: 0.7-0.8 of the link)
+        self.d_pose_in = [torch.empty_like(batch.poses) for _ in range(2)]
+        self.d_k_in = [torch.empty_like(batch.k) for _ in range(2)]
+        self.params_ev = [torch.cuda.Event() for _ in range(2)]
+        self.params_done = [None, None]            # compute stream has moved staging [parity] into place
+        self.parity = 0
         self.launches_per_step = {"u8": 3 * len(self.chunk_events) + 2, "u8t": 3 * len(self.chunk_events) + 2,
                                   "raw": 3 * len(problems) + 2, "packed": 2, "params": 2}
 
@@ -238,7 +246,14 @@ class HostStaged:
             ing, arena = (self.ingest, self.arena) if mode == "u8" else (self.ingest_t, self.arena_t)
             if len(self.consumed) != len(self.chunk_events):
                 self.consumed = [None] * len(self.chunk_events)
+            par = self.parity
+            self.parity ^= 1
             with torch.cuda.stream(cs):
+                if self.params_done[par] is not None:
+                    cs.wait_event(self.params_done[par])
+                self.d_pose_in[par].copy_(self.h_pose, non_blocking=True)
+                self.d_k_in[par].copy_(self.h_k, non_blocking=True)
+                self.params_ev[par].record(cs)
                 for c, ev in enumerate(self.chunk_events):
                     first = c * self.chunk
                     if self.consumed[c] is not None:
@@ -277,8 +292,16 @@ class HostStaged:
             for devs, hosts in zip(self.packed_dev, self.packed_host):
                 for d, h in zip(devs, hosts):
                     d.copy_(h, non_blocking=True)
-        b.poses.copy_(self.h_pose, non_blocking=True)
-        b.k.copy_(self.h_k, non_blocking=True)
+        if mode in ("u8", "u8t"):
+            main.wait_event(self.params_ev[par])
+            b.poses.copy_(self.d_pose_in[par], non_blocking=True)
+            b.k.copy_(self.d_k_in[par], non_blocking=True)
+            if self.params_done[par] is None:
+                self.params_done[par] = torch.cuda.Event()
+            self.params_done[par].record(main)
+        else:
+            b.poses.copy_(self.h_pose, non_blocking=True)
+            b.k.copy_(self.h_k, non_blocking=True)
         b.gn_step()
         self.o_pose.copy_(b.poses, non_blocking=True)
         self.o_k.copy_(b.k, non_blocking=True)
@@ -673,11 +696,19 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM bytes of the fused kernel per launch come from an ncu capture (profiles/traffic.json); the figure is only
+        # reported when it was captured on exactly this source tree (hash of csrc/ + the header), else null
+        traffic, traffic_note = None, "no ncu capture for this source tree"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(f"{args.mode}_bytes_per_launch_{args.pairs}pairs")
+                import __graft_entry__ as entry
+                tj = json.load(open(tp))
+                if tj.get("lib_hash") == entry.source_hash():
+                    traffic = tj.get(f"{args.mode}_bytes_per_launch_{args.pairs}pairs")
+                    traffic_note = tj.get("source")
+                else:
+                    traffic_note = "profiles/traffic.json was captured on a different source tree (hash mismatch)"
             except Exception:
                 traffic = None
         cpu_baseline = None
@@ -700,7 +731,8 @@ def main():
                            "parallelism": f"shard{world}",
                            "working_set_bytes_per_gpu": int(ws), "l2": "inputs larger than L2 (126 MB), no flush"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
+                             "peak_source": peak_src,
                              "kernel": "k_align_global<GN>" if args.mode == "gn" else "k_align_global<GRAD>",
                              "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": int(alg_bytes)},
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}

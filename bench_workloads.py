@@ -440,6 +440,24 @@ def run_c4(ctx):
         return (out,)
 
     chk = shard_check(ctx, n_units, rerun, (gathered,), "per-frame checksums of the completed depth map")
+    cpu_baseline = None
+    if ctx.rank == 0 and ctx.world == 1 and not a.no_cpu_baseline:
+        # the reference's own per-frame path on the host cores (oracle/ref_port.py restates it operation for operation:
+        # odometery/depth_init.py:10-67 + depth_completion/segment_based_completion.py:48-54,21-27), a bounded sample
+        from oracle import ref_port as port
+        kf_c, sp_c = frames[0][0].to("cpu"), frames[0][1].cpu()
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+        with torch.no_grad():
+            port.completion_render(kf_c, *port.segment_median_reinit(sp_c, kf_c, 'median'))       # warm-up
+            t0 = time.perf_counter()
+            n_cpu = 3
+            for _ in range(n_cpu):
+                kk, vis = port.segment_median_reinit(sp_c, kf_c, 'median')
+                port.completion_render(kf_c, kk, vis)
+            dt = (time.perf_counter() - t0) / n_cpu
+        cpu_baseline = {"value": 1.0 / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{n_cpu} frames (after 1 warm-up) of per-segment median re-initialisation + dense depth "
+                                  f"expansion + average render on the host, {dt * 1e3:.0f} ms per frame"}
     if ctx.rank == 0:
         peak, src = hbm_peak()
         P = geom.P
@@ -458,6 +476,7 @@ def run_c4(ctx):
                             "algorithmic_bytes_per_frame": int(bytes_frame),
                             "note": "whole per-frame pipeline time incl. its two host syncs per frame (point count, visible count)"}
         line["shard_check"] = chk
+        line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
 
 

@@ -91,10 +91,16 @@ typedef struct SpbStats {
  * Replaces the first half of torch.where in core/dense_optim.py:98-103. */
 int spb_compact_count(const uint8_t* masks, int N, int H, int W, int32_t* row_cnt, void* stream);
 
-/* Pass 2: exclusive scan of row counts -> row offsets in the padded point array, CSR pointers.
- * totals[0] = P (unpadded), totals[1] = padded length. Single CTA. */
+/* Pass 2: exclusive scan of row counts -> row offsets in the padded point array, CSR pointers of the segments and
+ * of their tiles (seg_tile [N+1], may be NULL; a tile never straddles segments).
+ * totals[0] = P (unpadded), totals[1] = padded length, totals[2] = number of tiles. Single CTA. */
 int spb_compact_scan(const int32_t* row_cnt, int N, int H, int32_t* row_off, int32_t* seg_ptr,
-                     int32_t* seg_ptr_pad, int32_t* totals, void* stream);
+                     int32_t* seg_ptr_pad, int32_t* seg_tile, int32_t* totals, void* stream);
+
+/* The tile table [n_tiles][4] = {segment, padded start, count, unpadded start} from the CSR pointers of pass 2
+ * (device arrays), built on the device so the keyframe build reads back three integers only. */
+int spb_tile_table(const int32_t* seg_ptr, const int32_t* seg_ptr_pad, const int32_t* seg_tile, int N,
+                   int32_t* tiles, void* stream);
 
 /* Pass 3: ordered scatter (segment,row,col order == torch.where order) of packed pixel
  * coordinates and raw log-depth; also the per-segment keypoint pixel and log-depth at the

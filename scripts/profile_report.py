@@ -52,6 +52,9 @@ for mode in ("gn", "grad"):
         traffic[f"{mode}_bytes_per_launch_64pairs"] = rd + wr
 if traffic and "_" not in tag:      # variant visits (<variant>_<tag>) never replace the default library's traffic figure
     traffic["source"] = f"ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, visit {tag}"
+    sys.path.insert(0, root)
+    import __graft_entry__ as entry
+    traffic["lib_hash"] = entry.source_hash()      # bench.py reports the figure only for this exact source tree
     json.dump(traffic, open(f"{out}/traffic.json", "w"), indent=1)
 lines = []
 for name in sorted(os.listdir(src)):

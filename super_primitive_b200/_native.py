@@ -71,7 +71,8 @@ class SpbWindow(C.Structure):
 _vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 _PROTOS = {
     "spb_compact_count": (_i, [_vp, _i, _i, _i, _vp, _vp]),
-    "spb_compact_scan": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "spb_compact_scan": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spb_tile_table": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "spb_compact_fill": (_i, [_vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spb_pack_rgba": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
     "spb_sample_source": (_i, [C.POINTER(SpbGeom), _vp, _i, _i, _vp, _vp]),

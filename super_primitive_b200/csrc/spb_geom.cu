@@ -5,61 +5,94 @@
 #include "spb_frame_stages.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// compaction pass 1: one warp per (segment,row): popcount of the row
+// compaction pass 1: one warp per (segment,row): number of mask pixels in the row.
+// The masks are N*H*W bytes (the largest thing the build reads: 31 MB at 640x480x100, 201 MB at 1024x768x256) and are
+// almost everywhere zero (a segment covers ~1/N of the image), so both passes over them read 16 mask bytes per lane
+// and per load when the rows are 16-byte aligned (W % 16 == 0: every shape the callers produce).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nonzero_bytes(uint32_t w) { return __popc(__vcmpne4(w, 0u) & 0x01010101u); }
+// 4-bit mask of the non-zero bytes of a word (bit j = byte j)
+__device__ __forceinline__ uint32_t nonzero_mask4(uint32_t w) {
+    return (((__vcmpne4(w, 0u) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
+}
+
+template <bool VEC>
 __global__ void k_row_count(const uint8_t* __restrict__ masks, int rows, int W, int32_t* __restrict__ row_cnt) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const uint8_t* m = masks + (size_t)row * W;
     int n = 0;
-    for (int x = lane; x < W; x += 32) n += (m[x] != 0);
+    if constexpr (VEC) {
+        const uint4* m16 = reinterpret_cast<const uint4*>(m);
+        for (int i = lane; i < (W >> 4); i += 32) {
+            const uint4 v = __ldg(m16 + i);
+            n += nonzero_bytes(v.x) + nonzero_bytes(v.y) + nonzero_bytes(v.z) + nonzero_bytes(v.w);
+        }
+    } else {
+        for (int x = lane; x < W; x += 32) n += (m[x] != 0);
+    }
     n = __reduce_add_sync(0xffffffffu, n);
     if (lane == 0) row_cnt[row] = n;
 }
 
-// pass 2: single-CTA scan over N*H row counts with per-segment padding to SPB_PAD
-__global__ void k_row_scan(const int32_t* __restrict__ row_cnt, int N, int H, int32_t* __restrict__ row_off,
-                           int32_t* __restrict__ seg_ptr, int32_t* __restrict__ seg_ptr_pad,
-                           int32_t* __restrict__ totals) {
-    // phase A: per-segment totals (thread per segment, strided)
+// pass 2: one CTA; a warp per segment sums its H row counts (coalesced), one thread lays the segments out with their
+// padding to SPB_PAD, then a warp per segment turns the row counts into row offsets with a shuffle scan
+__global__ void __launch_bounds__(1024)
+k_row_scan(const int32_t* __restrict__ row_cnt, int N, int H, int32_t* __restrict__ row_off,
+           int32_t* __restrict__ seg_ptr, int32_t* __restrict__ seg_ptr_pad, int32_t* __restrict__ seg_tile,
+           int32_t* __restrict__ totals) {
     extern __shared__ int32_t s_seg[];       // [N] counts -> padded starts
-    for (int b = threadIdx.x; b < N; b += blockDim.x) {
-        int n = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int b = warp; b < N; b += nwarps) {
         const int32_t* r = row_cnt + (size_t)b * H;
-        for (int y = 0; y < H; ++y) n += r[y];
-        s_seg[b] = n;
+        int n = 0;
+        for (int y = lane; y < H; y += 32) n += r[y];
+        n = __reduce_add_sync(0xffffffffu, n);
+        if (lane == 0) s_seg[b] = n;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int run = 0, run_pad = 0;
+        int run = 0, run_pad = 0, run_tile = 0;
         for (int b = 0; b < N; ++b) {
             const int n = s_seg[b];
             seg_ptr[b] = run;
             seg_ptr_pad[b] = run_pad;
+            if (seg_tile) seg_tile[b] = run_tile;
             s_seg[b] = run_pad;
             run += n;
             run_pad += (n + SPB_PAD - 1) / SPB_PAD * SPB_PAD;
+            run_tile += (n + SPB_TILE - 1) / SPB_TILE;             // tiles never straddle segments
         }
         seg_ptr[N] = run;
         seg_ptr_pad[N] = run_pad;
+        if (seg_tile) seg_tile[N] = run_tile;
         totals[0] = run;
         totals[1] = run_pad;
+        totals[2] = run_tile;
     }
     __syncthreads();
-    // phase B: row offsets inside each segment
-    for (int b = threadIdx.x; b < N; b += blockDim.x) {
+    for (int b = warp; b < N; b += nwarps) {
         int off = s_seg[b];
         const int32_t* r = row_cnt + (size_t)b * H;
         int32_t* o = row_off + (size_t)b * H;
-        for (int y = 0; y < H; ++y) {
-            o[y] = off;
-            off += r[y];
+        for (int y0 = 0; y0 < H; y0 += 32) {
+            const int y = y0 + lane;
+            const int c = y < H ? r[y] : 0;
+            int incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (y < H) o[y] = off + incl - c;
+            off += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
 }
 
 // pass 3: ordered scatter, one warp per (segment,row)
+template <bool VEC>
 __global__ void k_row_fill(const uint8_t* __restrict__ masks, const float* __restrict__ logd, int64_t seg_stride,
                            int N, int H, int W, const int32_t* __restrict__ row_off, uint32_t* __restrict__ uv,
                            float* __restrict__ L) {
@@ -75,17 +108,48 @@ __global__ void k_row_fill(const uint8_t* __restrict__ masks, const float* __res
     const float tih = 2.0f * (1.0f / (float)(H - 1));
     const bool yok = fabsf(fmaf((float)y, tih, -1.0f)) <= 0.99f;
     int off = row_off[row];
-    for (int x0 = 0; x0 < W; x0 += 32) {
-        const int x = x0 + lane;
-        const bool on = (x < W) && (m[x] != 0);
-        const unsigned bal = __ballot_sync(0xffffffffu, on);
-        if (on) {
-            const int dst = off + __popc(bal & ((1u << lane) - 1u));
-            const bool ok = yok && (fabsf(fmaf((float)x, tiw, -1.0f)) <= 0.99f);
-            uv[dst] = (uint32_t)x | ((uint32_t)y << 16) | (ok ? 0x80000000u : 0u);
-            L[dst] = lrow[x];
+    if constexpr (VEC) {
+        const uint4* m16 = reinterpret_cast<const uint4*>(m);
+        const int W16 = W >> 4;
+        for (int i0 = 0; i0 < W16; i0 += 32) {
+            const int i = i0 + lane;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (i < W16) v = __ldg(m16 + i);
+            uint32_t bits = nonzero_mask4(v.x) | (nonzero_mask4(v.y) << 4) | (nonzero_mask4(v.z) << 8) |
+                            (nonzero_mask4(v.w) << 12);
+            const int c = __popc(bits);
+            if (!__any_sync(0xffffffffu, c != 0)) continue;          // 512 empty pixels: the common case
+            int incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            int dst = off + incl - c;
+            off += __shfl_sync(0xffffffffu, incl, 31);
+            while (bits) {
+                const int j = __ffs((int)bits) - 1;
+                bits &= bits - 1u;
+                const int x = (i << 4) + j;
+                const bool ok = yok && (fabsf(fmaf((float)x, tiw, -1.0f)) <= 0.99f);
+                uv[dst] = (uint32_t)x | ((uint32_t)y << 16) | (ok ? 0x80000000u : 0u);
+                L[dst] = lrow[x];
+                ++dst;
+            }
         }
-        off += __popc(bal);
+    } else {
+        for (int x0 = 0; x0 < W; x0 += 32) {
+            const int x = x0 + lane;
+            const bool on = (x < W) && (m[x] != 0);
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            if (on) {
+                const int dst = off + __popc(bal & ((1u << lane) - 1u));
+                const bool ok = yok && (fabsf(fmaf((float)x, tiw, -1.0f)) <= 0.99f);
+                uv[dst] = (uint32_t)x | ((uint32_t)y << 16) | (ok ? 0x80000000u : 0u);
+                L[dst] = lrow[x];
+            }
+            off += __popc(bal);
+        }
     }
 }
 
@@ -111,17 +175,38 @@ __global__ void k_keypoints(const float* __restrict__ keypoints, const float* __
 extern "C" int spb_compact_count(const uint8_t* masks, int N, int H, int W, int32_t* row_cnt, void* stream) {
     if (!masks || !row_cnt || N < 1 || H < 2 || W < 2 || H > 32767 || W > 65535) return SPB_EINVAL;
     const int rows = N * H;
-    k_row_count<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(masks, rows, W, row_cnt);
+    if (W % 16 == 0 && (reinterpret_cast<uintptr_t>(masks) & 15u) == 0)
+        k_row_count<true><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(masks, rows, W, row_cnt);
+    else
+        k_row_count<false><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(masks, rows, W, row_cnt);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
 
 extern "C" int spb_compact_scan(const int32_t* row_cnt, int N, int H, int32_t* row_off, int32_t* seg_ptr,
-                                int32_t* seg_ptr_pad, int32_t* totals, void* stream) {
+                                int32_t* seg_ptr_pad, int32_t* seg_tile, int32_t* totals, void* stream) {
     if (!row_cnt || !row_off || !seg_ptr || !seg_ptr_pad || !totals || N < 1 || H < 1) return SPB_EINVAL;
     if ((size_t)N * sizeof(int32_t) > 48 * 1024) return SPB_ELIMIT;
-    k_row_scan<<<1, 512, N * sizeof(int32_t), (cudaStream_t)stream>>>(row_cnt, N, H, row_off, seg_ptr, seg_ptr_pad,
-                                                                      totals);
+    k_row_scan<<<1, 1024, N * sizeof(int32_t), (cudaStream_t)stream>>>(row_cnt, N, H, row_off, seg_ptr, seg_ptr_pad,
+                                                                       seg_tile, totals);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+// tile table: one CTA per segment writes {segment, padded start, count, unpadded start} of its tiles
+__global__ void k_tile_table(const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_ptr_pad,
+                             const int32_t* __restrict__ seg_tile, int32_t* __restrict__ tiles) {
+    const int b = blockIdx.x;
+    const int cnt = seg_ptr[b + 1] - seg_ptr[b], t0 = seg_tile[b], nt = seg_tile[b + 1] - t0;
+    int4* out = reinterpret_cast<int4*>(tiles) + t0;
+    for (int j = threadIdx.x; j < nt; j += blockDim.x)
+        out[j] = make_int4(b, seg_ptr_pad[b] + j * SPB_TILE, min(cnt - j * SPB_TILE, SPB_TILE), seg_ptr[b] + j * SPB_TILE);
+}
+
+extern "C" int spb_tile_table(const int32_t* seg_ptr, const int32_t* seg_ptr_pad, const int32_t* seg_tile, int N,
+                              int32_t* tiles, void* stream) {
+    if (!seg_ptr || !seg_ptr_pad || !seg_tile || !tiles || N < 1) return SPB_EINVAL;
+    k_tile_table<<<N, 128, 0, (cudaStream_t)stream>>>(seg_ptr, seg_ptr_pad, seg_tile, tiles);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
@@ -132,7 +217,10 @@ extern "C" int spb_compact_fill(const uint8_t* masks, const float* logd, int64_t
     if (!masks || !logd || !keypoints || !row_off || !uv || !L || !seg_lkp || !kp_rc) return SPB_EINVAL;
     const int rows = N * H;
     cudaStream_t st = (cudaStream_t)stream;
-    k_row_fill<<<(rows + 7) / 8, 256, 0, st>>>(masks, logd, logd_seg_stride, N, H, W, row_off, uv, L);
+    if (W % 16 == 0 && (reinterpret_cast<uintptr_t>(masks) & 15u) == 0)
+        k_row_fill<true><<<(rows + 7) / 8, 256, 0, st>>>(masks, logd, logd_seg_stride, N, H, W, row_off, uv, L);
+    else
+        k_row_fill<false><<<(rows + 7) / 8, 256, 0, st>>>(masks, logd, logd_seg_stride, N, H, W, row_off, uv, L);
     SPB_CHECK_LAUNCH();
     k_keypoints<<<(N + 127) / 128, 128, 0, st>>>(keypoints, logd, logd_seg_stride, N, H, W, seg_lkp, kp_rc);
     SPB_CHECK_LAUNCH();

@@ -62,18 +62,16 @@ class CompactGeometry:
         i32 = dict(dtype=torch.int32, device=dev)
         row_cnt = torch.empty(N * H, **i32)
         row_off = torch.empty(N * H, **i32)
-        seg_ptr = torch.empty(N + 1, **i32)
-        seg_ptr_pad = torch.empty(N + 1, **i32)
-        totals = torch.empty(2, **i32)
+        csr = torch.empty(3 * (N + 1) + 3, **i32)          # seg_ptr | seg_ptr_pad | seg_tile | totals, one allocation
+        seg_ptr, seg_ptr_pad, seg_tile = csr[:N + 1], csr[N + 1:2 * (N + 1)], csr[2 * (N + 1):3 * (N + 1)]
+        totals = csr[3 * (N + 1):]
         nat.check(lib.spb_compact_count(m8.data_ptr(), N, H, W, row_cnt.data_ptr(), st), "spb_compact_count")
         nat.check(lib.spb_compact_scan(row_cnt.data_ptr(), N, H, row_off.data_ptr(), seg_ptr.data_ptr(),
-                                       seg_ptr_pad.data_ptr(), totals.data_ptr(), st), "spb_compact_scan")
-        # one host sync per keyframe: the point count sizes the allocations (the reference syncs on
-        # torch.where every iteration)
-        host = torch.cat([totals, seg_ptr, seg_ptr_pad]).cpu().numpy()
-        P, P_pad = int(host[0]), int(host[1])
-        sp = host[2:2 + N + 1].astype(np.int64)
-        spp = host[2 + N + 1:].astype(np.int64)
+                                       seg_ptr_pad.data_ptr(), seg_tile.data_ptr(), totals.data_ptr(), st),
+                  "spb_compact_scan")
+        # one host sync per keyframe: three integers size the allocations (the reference syncs on torch.where every
+        # iteration); the segment pointers stay on the device and are fetched lazily for the statistics path
+        P, P_pad, T = (int(v) for v in totals.tolist())
         if P <= 0:
             raise AssertionError("keyframe has no segment pixels")
         self.N, self.H, self.W, self.P, self.P_pad = N, H, W, P, P_pad
@@ -84,24 +82,14 @@ class CompactGeometry:
         nat.check(lib.spb_compact_fill(m8.data_ptr(), logd_c.data_ptr(), H * W if per_seg else 0, kps.data_ptr(),
                                        N, H, W, row_off.data_ptr(), self.uv.data_ptr(), self.logd.data_ptr(),
                                        self.seg_lkp.data_ptr(), self.kp_rc.data_ptr(), st), "spb_compact_fill")
-        # tile table (host, once): tiles never straddle segments
-        cnt = sp[1:] - sp[:-1]
-        ntile = (cnt + nat.TILE - 1) // nat.TILE
-        seg_tile = np.zeros(N + 1, dtype=np.int64)
-        np.cumsum(ntile, out=seg_tile[1:])
-        T = int(seg_tile[-1])
-        seg_of = np.repeat(np.arange(N), ntile)
-        j = np.arange(T) - seg_tile[seg_of]
-        tiles = np.empty((T, 4), dtype=np.int32)
-        tiles[:, 0] = seg_of
-        tiles[:, 1] = spp[seg_of] + j * nat.TILE
-        tiles[:, 2] = np.minimum(cnt[seg_of] - j * nat.TILE, nat.TILE)
-        tiles[:, 3] = sp[seg_of] + j * nat.TILE
+        # tile table on the device: tiles never straddle segments
         self.n_tiles = T
-        self.tiles = torch.from_numpy(tiles).to(dev)
-        self.seg_tile = torch.from_numpy(seg_tile.astype(np.int32)).to(dev)
-        self.seg_ptr_host = sp
-        self.seg_ptr_pad_host = spp
+        self.tiles = torch.empty((T, 4), **i32)
+        self.seg_tile = seg_tile
+        nat.check(lib.spb_tile_table(seg_ptr.data_ptr(), seg_ptr_pad.data_ptr(), seg_tile.data_ptr(), N,
+                                     self.tiles.data_ptr(), st), "spb_tile_table")
+        self._csr = csr
+        self._seg_ptr_host = None
         self._pad_index = None
         self._seg_ids = None
         self.c = nat.SpbGeom(self.uv.data_ptr(), self.logd.data_ptr(), self.tiles.data_ptr(),
@@ -112,6 +100,18 @@ class CompactGeometry:
         self._work = {}
 
     # ---- helpers -------------------------------------------------------------------------------
+    @property
+    def seg_ptr_host(self):
+        if self._seg_ptr_host is None:
+            h = self._csr[:2 * (self.N + 1)].cpu().numpy().astype(np.int64)
+            self._seg_ptr_host = (h[:self.N + 1], h[self.N + 1:])
+        return self._seg_ptr_host[0]
+
+    @property
+    def seg_ptr_pad_host(self):
+        self.seg_ptr_host
+        return self._seg_ptr_host[1]
+
     def pad_index(self):
         """(P,) int64: position of every unpadded point in the padded arrays."""
         if self._pad_index is None:

@@ -21,26 +21,27 @@ def owner_of(unit, world):
     return unit % world
 
 
-def gather_results(poses, k_padded, costs, n_units, group=None):
+def gather_results(poses, k_padded, costs, n_units, group=None, device=None):
     """All ranks contribute their local results; every rank receives the global, unit-ordered
     (poses (n,4,4), k (n,Nmax) NaN-padded, costs (n,)).  Local arrays are ordered like
-    ``shard_indices``."""
+    ``shard_indices``.  A rank whose shard is empty (n_units < world) passes ``None`` for the three arrays (and the
+    ``device`` its collectives run on): it still takes part in every collective."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return poses, k_padded, costs
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    dev = poses.device
+    dev = poses.device if poses is not None else torch.device(device if device is not None else "cpu")
     n_local_max = (n_units + world - 1) // world
+    n_local = 0 if poses is None else poses.shape[0]
     # agree on the padded segment count
-    nmax = torch.tensor([k_padded.shape[1]], dtype=torch.int64, device=dev)
+    nmax = torch.tensor([k_padded.shape[1] if n_local else 0], dtype=torch.int64, device=dev)
     dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=group)
     nmax = int(nmax.item())
     width = 16 + nmax + 1
     payload = torch.full((n_local_max, width), float('nan'), dtype=torch.float32, device=dev)
-    n_local = poses.shape[0]
-    payload[:n_local, :16] = poses.reshape(n_local, 16)
-    payload[:n_local, 16:16 + k_padded.shape[1]] = k_padded
-    payload[:n_local, 16 + nmax] = costs
+    if n_local:
+        payload[:n_local, :16] = poses.reshape(n_local, 16)
+        payload[:n_local, 16:16 + k_padded.shape[1]] = k_padded
+        payload[:n_local, 16 + nmax] = costs
     gathered = [torch.empty_like(payload) for _ in range(world)]
     dist.all_gather(gathered, payload, group=group)
     out_pose = torch.empty((n_units, 4, 4), dtype=torch.float32, device=dev)
@@ -58,7 +59,7 @@ def gather_results(poses, k_padded, costs, n_units, group=None):
     return out_pose, out_k, out_cost
 
 
-def gather_ragged(vectors, n_units, group=None):
+def gather_ragged(vectors, n_units, group=None, device=None):
     """Variable-length results (one 1-D float32 tensor per LOCAL unit, ordered like ``shard_indices``) -> list of
     ``n_units`` tensors in unit order on every rank.  Used for mapping windows, whose result (frame poses, seeds of
     every keyframe, brightness terms, loss) has a window-dependent length: two all-reduces agree on the padded
@@ -66,7 +67,7 @@ def gather_ragged(vectors, n_units, group=None):
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return list(vectors)
     world = dist.get_world_size(group)
-    dev = vectors[0].device if vectors else torch.device("cpu")
+    dev = vectors[0].device if vectors else torch.device(device if device is not None else "cpu")   # empty shard: say where
     n_local_max = (n_units + world - 1) // world
     width = torch.tensor([max((int(v.numel()) for v in vectors), default=0)], dtype=torch.int64, device=dev)
     dist.all_reduce(width, op=dist.ReduceOp.MAX, group=group)

@@ -30,13 +30,16 @@ def _worker(rank, world, port, n_units, q):
         for i, u in enumerate(idx):
             k[i, :3 + u % 4] = torch.arange(3 + u % 4, dtype=torch.float32) + 10 * u
         cost = torch.tensor([0.5 * u for u in idx], dtype=torch.float32)
-        P, K, Cst = gather_results(poses, k, cost, n_units)
+        if idx:
+            P, K, Cst = gather_results(poses, k, cost, n_units)
+        else:       # an empty shard (fewer units than ranks): no batch was ever built on this rank
+            P, K, Cst = gather_results(None, None, None, n_units, device="cpu")
         q.put((rank, P.numpy(), K.numpy(), Cst.numpy()))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_units", [5, 8])
+@pytest.mark.parametrize("n_units", [1, 5, 8])
 def test_gather_world2(n_units):
     world = 2
     ctx = mp.get_context("spawn")
@@ -66,13 +69,13 @@ def _ragged_worker(rank, world, port, n_units, q):
     try:
         # unit u (a mapping window) has a result of 5 + 3 * (u % 3) floats
         vecs = [torch.arange(5 + 3 * (u % 3), dtype=torch.float32) + 100 * u for u in shard_indices(n_units, rank, world)]
-        out = gather_ragged(vecs, n_units)
+        out = gather_ragged(vecs, n_units, device="cpu")
         q.put((rank, [o.numpy() for o in out]))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_units", [3, 6])
+@pytest.mark.parametrize("n_units", [1, 3, 6])
 def test_gather_ragged_world2(n_units):
     """Mapping windows have window-dependent result lengths: NaN-padded rows + lengths, one all-gather."""
     world = 2
