@@ -438,8 +438,10 @@ def time_dropin_single_pair(device, iters=60, warm=10):
     wall = time.perf_counter() - t0
     return {"iters_per_s": iters / wall, "ms_per_iter_wall": wall / iters * 1e3,
             "ms_per_iter_device": a.elapsed_time(b) / iters,
-            "what": "reference loop through the drop-in API on ONE pair (forward+backward kernel, finiteness check "
-                    "= 1 host sync, Adam.step); host/launch-bound"}
+            "what": "reference loop through the drop-in API on ONE pair: photomeric_cost (one fused forward+backward launch + "
+                    "finalize, finiteness flags read every 16 calls) -> backward -> torch.optim.Adam.step; host-bound by "
+                    "PyTorch itself (Adam.step alone ~150 us, the autograd engine ~100 us, this package's forward ~100 us: "
+                    "profiles/r02c_dropin_profile.txt)"}
 
 
 def time_device_loop_single_pair(device, iters=200):
@@ -629,14 +631,20 @@ def main():
 
         v_u8 = timed("u8")
         # what the link itself delivers: the same pinned arena copied to the staging buffer with nothing else going on
+        # every rank copies at the same time (barrier first): with several GPUs this is the CONCURRENT ceiling of the
+        # host links, the slowest rank's figure is the one the fraction is taken against
         hs.copy_stream.synchronize()
+        barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
         for _ in range(5):
             hs.ingest.upload(hs.arena)
         p1.record()
         torch.cuda.synchronize()
-        h2d_gbps = 5 * hs.ingest.offsets[-1] / (p0.elapsed_time(p1) * 1e-3) / 1e9
+        lt = torch.tensor([5 * hs.ingest.offsets[-1] / (p0.elapsed_time(p1) * 1e-3) / 1e9], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(lt, op=dist.ReduceOp.MIN)
+        h2d_gbps = float(lt.item())
         v_u8t = timed("u8t")            # informational: the odometry case, only the new frame of every pair travels
         v_raw = timed("raw")            # informational: frames converted to float32 on the host (the reference's image_tt)
         v_packed = timed("packed")      # informational: derived buffers uploaded instead of frames
