@@ -342,9 +342,11 @@ int spb_depth_splat_points(const float* pts, int P, const float* K, int H, int W
 int spb_depth_avg_dense(float* depths, int N, int H, int W, float* out, uint8_t* invalid, void* stream);
 
 /* The same result straight from the compact geometry (lines 48-54 fused: unproject_kf_to_depths, mask, drop the
- * segments with visible[b] == 0, average) without materialising (N,H,W); sum/cnt: [H*W] float scratch. */
-int spb_depth_avg_compact(const SpbGeom* geom, const float* k, const uint8_t* visible, float* sum, float* cnt,
-                          float* out, uint8_t* invalid, void* stream);
+ * segments with visible[b] == 0, average) without materialising (N,H,W).  Scratch: sum [H*W] 64-bit (32.32 fixed-point
+ * accumulation with integer atomics: independent of the order in which overlapping segments arrive, bit-reproducible),
+ * cnt [H*W] 32-bit. */
+int spb_depth_avg_compact(const SpbGeom* geom, const float* k, const uint8_t* visible, unsigned long long* sum,
+                          uint32_t* cnt, float* out, uint8_t* invalid, void* stream);
 
 /* One image-pyramid step (image/gaussian_pyramid.py:53-85): dst (C, ceil(H/2), ceil(W/2)) = 3x3 [1 2 1]^2/16 blur
  * with reflect padding of src (C,H,W), decimated [::2, ::2]. */

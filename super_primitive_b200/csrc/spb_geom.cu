@@ -485,10 +485,14 @@ __global__ void k_depth_avg_dense(float* __restrict__ depths, int N, int HW, flo
     }
 }
 
-// fused variant straight from the compact geometry: no (N,H,W) tensor is ever materialised
+// fused variant straight from the compact geometry: no (N,H,W) tensor is ever materialised.
+// Overlapping segments add into the same pixel from different warps: the sum is accumulated in 32.32 fixed point with
+// 64-bit integer atomics and the count with 32-bit ones, so the result does not depend on the order of arrival
+// (bit-reproducible, and the same on any number of GPUs); the exact sum is rounded to float32 once.
+#define SPB_AVG_FX 4294967296.0   /* 2^32 */
 __global__ void k_depth_avg_compact(const __grid_constant__ SpbGeom g, const float* __restrict__ k,
-                                    const uint8_t* __restrict__ visible, float* __restrict__ sum,
-                                    float* __restrict__ cnt) {
+                                    const uint8_t* __restrict__ visible, unsigned long long* __restrict__ sum,
+                                    uint32_t* __restrict__ cnt) {
     const int lane = threadIdx.x & 31;
     const int wglobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int wstride = gridDim.x * (blockDim.x >> 5);
@@ -502,19 +506,19 @@ __global__ void k_depth_avg_compact(const __grid_constant__ SpbGeom g, const flo
             const uint32_t w = g.uv[p];
             const int u = (int)(w & 0xffffu), v = (int)((w >> 16) & 0x7fffu);
             const float z = expf(g.logd[p] + shift);
-            if (z > 1e-6f) {
-                atomicAdd(sum + (size_t)v * g.W + u, z);
-                atomicAdd(cnt + (size_t)v * g.W + u, 1.0f);
+            if (z > 1e-6f && z < 2.0e9f) {
+                atomicAdd(sum + (size_t)v * g.W + u, (unsigned long long)((double)z * SPB_AVG_FX + 0.5));
+                atomicAdd(cnt + (size_t)v * g.W + u, 1u);
             }
         }
     }
 }
 
-__global__ void k_depth_avg_resolve(const float* __restrict__ sum, const float* __restrict__ cnt, int HW,
+__global__ void k_depth_avg_resolve(const unsigned long long* __restrict__ sum, const uint32_t* __restrict__ cnt, int HW,
                                     float* __restrict__ out, uint8_t* __restrict__ invalid) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-        out[i] = sum[i] / (cnt[i] + 1e-6f);
-        invalid[i] = cnt[i] == 0.f;
+        out[i] = (float)((double)sum[i] * (1.0 / SPB_AVG_FX)) / ((float)cnt[i] + 1e-6f);
+        invalid[i] = cnt[i] == 0u;
     }
 }
 
@@ -528,14 +532,14 @@ extern "C" int spb_depth_avg_dense(float* depths, int N, int H, int W, float* ou
     return SPB_OK;
 }
 
-extern "C" int spb_depth_avg_compact(const SpbGeom* geom, const float* k, const uint8_t* visible, float* sum,
-                                     float* cnt, float* out, uint8_t* invalid, void* stream) {
+extern "C" int spb_depth_avg_compact(const SpbGeom* geom, const float* k, const uint8_t* visible,
+                                     unsigned long long* sum, uint32_t* cnt, float* out, uint8_t* invalid, void* stream) {
     if (!geom || !k || !sum || !cnt || !out || !invalid || geom->n_tiles < 1) return SPB_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = geom->H * geom->W;
-    cudaError_t e = cudaMemsetAsync(sum, 0, sizeof(float) * (size_t)HW, st);
+    cudaError_t e = cudaMemsetAsync(sum, 0, sizeof(unsigned long long) * (size_t)HW, st);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(cnt, 0, sizeof(float) * (size_t)HW, st);
+    e = cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * (size_t)HW, st);
     if (e != cudaSuccess) return (int)e;
     k_depth_avg_compact<<<lift_blocks(geom->n_tiles), 256, 0, st>>>(*geom, k, visible, sum, cnt);
     SPB_CHECK_LAUNCH();

@@ -37,8 +37,8 @@ def render_segments_avg(kf, keypoint_logdepth, visible_seg=None):
         if visible_seg is not None:
             vis = (visible_seg if visible_seg.dtype == torch.bool else visible_seg != 0).contiguous().view(torch.uint8)
         HW = geom.H * geom.W
-        acc = torch.empty(HW, dtype=torch.float32, device=dev)
-        cnt = torch.empty(HW, dtype=torch.float32, device=dev)
+        acc = torch.empty(HW, dtype=torch.int64, device=dev)        # 32.32 fixed-point sums (order-independent atomics)
+        cnt = torch.empty(HW, dtype=torch.int32, device=dev)
         out = torch.empty((geom.H, geom.W), dtype=torch.float32, device=dev)
         invalid = torch.empty((geom.H, geom.W), dtype=torch.uint8, device=dev)
         nat.check(nat.lib().spb_depth_avg_compact(geom.cref, k_c.data_ptr(), nat.ptr(vis), acc.data_ptr(), cnt.data_ptr(),
