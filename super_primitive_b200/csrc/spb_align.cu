@@ -413,10 +413,14 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
 // Hot-path body: per-warp bulk-async pipelines (see spb_fast.cuh).  grid = (ctas_per_pair, pairs)
 //   part_pair : [cta][NACC]      part_seg : [tile][NSEG]
 // The warps of a CTA take adjacent tiles (their target footprints share L1 lines), CTAs stride over the pair.
-// Measured and dropped in round 2 (profiles/README.md, visit r02a): groups of 2-8 consecutive tiles per warp with one
-// partial-sum reduction per same-segment run (GN unchanged, gradient kernel slower: L1 locality), and touching the
+// Measured and dropped in round 2 (profiles/README.md, visits r02a, r02f): groups of 2-8 consecutive tiles per warp with
+// one partial-sum reduction per same-segment run (GN unchanged, gradient kernel slower: L1 locality); touching the
 // next point's predicted target row ahead of time with a 4-byte cp.async (the gathers already keep the L1 data path
-// 57 % busy; one more L1 access per point costs more than the latency it hides: l1tex 87 %, kernel 12 % slower).
+// 57 % busy; one more L1 access per point costs more than the latency it hides: l1tex 87 %, kernel 12 % slower); the
+// per-pair context in a __constant__ array indexed by blockIdx.y (nvcc emits vector-indexed LDC, which is slower than
+// the broadcast LDS it replaces: GN 0.430 vs 0.442, first-order 0.474 vs 0.599); staging only uv + logd in shared memory
+// and reading the cached source colours straight from global memory so that a tile can hold 256 points (r02g: GN
+// 0.444 = unchanged, first-order 0.461 vs 0.601: the stream's DRAM latency is no longer hidden by the bulk copy).
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int NP, bool AFF>
 __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair& pr, float irls_eps,
@@ -450,8 +454,8 @@ __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair&
     // producer (lane 0): ONE bulk copy brings the whole tile block (header + uv + logd + r + g + b)
     auto issue = [&](int t, int slot) {
         const uint32_t bar = smem_u32(bars + slot);
-        mbar_expect_tx(bar, SPB_PACK_WORDS * 4u);
-        bulk_g2s(smem_u32(ring + slot * SPB_SLOT_WORDS), pack + (size_t)t * SPB_PACK_WORDS, SPB_PACK_WORDS * 4u, bar);
+        mbar_expect_tx(bar, SPB_SLOT_WORDS * 4u);
+        bulk_g2s(smem_u32(ring + slot * SPB_SLOT_WORDS), pack + (size_t)t * SPB_PACK_WORDS, SPB_SLOT_WORDS * 4u, bar);
     };
     if (lane == 0) {
 #pragma unroll
@@ -577,6 +581,7 @@ k_align_global(const SpbGeom* __restrict__ geoms, const SpbPair* __restrict__ pa
     float* base = work + pair * work_stride;
     align_body_warp<MODE, NP, AFF>(s_g, s_pr, irls_eps, base, base + (size_t)gridDim.x * NACC);
 }
+
 
 // Fixed-order sum over the per-CTA partials [ctas][NACC] (contiguous): the block's threads form R = blockDim / NACC
 // row groups; thread (r, c) adds rows r, r + R, ... of column c (consecutive threads read consecutive floats, 8 loads

@@ -119,3 +119,27 @@ def test_host_staged_runs_every_mode_and_accounts_bytes(stubbed):
     assert hs.h2d["params"] == params and hs.d2h == (5 * 16 + 40 + 5 * 8) * 4
     assert hs.launches_per_step["u8"] == 3 * 3 + 2
     assert torch.equal(hs.ingest.stage, hs.arena)      # every chunk was uploaded
+
+
+def test_workload_helpers_are_deterministic_in_the_unit_id():
+    """bench_workloads: any rank can rebuild any unit from its id (the shard check relies on it)."""
+    import bench_workloads as bw
+    assert bw.grid_shape(64, 480, 640) == (8, 8) and bw.grid_shape(100, 224, 288) == (10, 10)
+    assert bw.grid_shape(256, 768, 1024) == (16, 16) and bw.grid_shape(300, 224, 288) == (20, 15)
+    a, b = bw.start_pose(17), bw.start_pose(17)
+    assert torch.equal(a, b) and not torch.equal(a, bw.start_pose(18))
+    assert set(bw.RUNNERS) == {"c2levels", "c3", "c4", "c5", "compaction"}
+
+
+def test_grid_sizing_fills_whole_waves():
+    """spb_gn_ctas (no GPU needed: the SM count falls back to 148): the CTA count per pair gives >= 3 waves with a last
+    wave >= 97 % full whenever the work allows, e.g. 27 CTAs x 64 pairs = 3.89 waves at 3 CTAs/SM, 3 x 1024 pairs = 6.92."""
+    from super_primitive_b200 import _native as nat
+    lib = nat.lib()
+    for tiles, pairs in ((4352, 64), (7100, 1024), (1100, 256), (4352, 128)):
+        c = lib.spb_gn_ctas(tiles, pairs)
+        assert 1 <= c <= (tiles + 7) // 8
+        # spb_gn_ctas is the maximum over the kernel variants (2, 3, 4 CTAs/SM); each variant's own grid is wave-aligned
+        assert pairs * c >= 3 * 148 * 2
+    assert lib.spb_gn_ctas(384, 1) == 48                         # few pairs: every warp gets one tile
+    assert lib.spb_gn_work_stride(4352, 64) >= lib.spb_gn_ctas(4352, 64) * 47 + 4352 * 19
