@@ -327,14 +327,15 @@ int spb_dense_depths(const uint8_t* masks, const float* logd, int64_t logd_seg_s
 /* estimate_depth_kf_native (core/depth_render.py:7-21 + core/ops.py:59-96): z-splat of the lifted
  * keyframe into view `pose`.  mean = 0: deterministic last-writer-wins in point order (the CPU
  * semantics of scatter_); mean = 1: scatter_reduce 'mean' including the initial zero.
- * keys: [H*W] uint64 scratch (zeroed by the call); out: [H][W]. */
+ * keys: [H*W] uint64 scratch (zeroed by the call); sum: [H*W] uint64 scratch, mean = 1 only (32.32 fixed-point sums
+ * added with integer atomics: order-independent, unlike the reference's scatter on a GPU); out: [H][W]. */
 int spb_depth_splat(const SpbGeom* geom, const float* k, const float* pose /* NULL = identity */,
-                    int mean, unsigned long long* keys, float* sum, float* out, void* stream);
+                    int mean, unsigned long long* keys, unsigned long long* sum, float* out, void* stream);
 
 /* estimate_depth_diff (core/ops.py:59-96) for an arbitrary point cloud pts [P][3] already in the target frame:
  * same splat semantics as spb_depth_splat; valid [P] (may be NULL) receives the reference's `valid_depth` mask. */
 int spb_depth_splat_points(const float* pts, int P, const float* K, int H, int W, int mean,
-                           unsigned long long* keys, float* sum, float* out, uint8_t* valid, void* stream);
+                           unsigned long long* keys, unsigned long long* sum, float* out, uint8_t* valid, void* stream);
 
 /* VOID depth-completion tail (depth_completion/segment_based_completion.py:21-27): per-pixel average of the valid
  * (>1e-6) entries of N stacked depth maps; entries <1e-6 are zeroed IN PLACE like the reference; invalid = no map

@@ -420,7 +420,8 @@ __device__ __forceinline__ void tile_reduce_store(float (&v)[N], float* __restri
 // per-pair context in a __constant__ array indexed by blockIdx.y (nvcc emits vector-indexed LDC, which is slower than
 // the broadcast LDS it replaces: GN 0.430 vs 0.442, first-order 0.474 vs 0.599); staging only uv + logd in shared memory
 // and reading the cached source colours straight from global memory so that a tile can hold 256 points (r02g: GN
-// 0.444 = unchanged, first-order 0.461 vs 0.601: the stream's DRAM latency is no longer hidden by the bulk copy).
+// 0.444 = unchanged, first-order 0.461 vs 0.601: the stream's DRAM latency is no longer hidden by the bulk copy); the
+// first-order kernel at 3 CTAs/SM, with or without the projection context hoisted into registers (r02h: 0.558 / 0.544).
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int NP, bool AFF>
 __device__ __forceinline__ void align_body_warp(const SpbGeom& g, const SpbPair& pr, float irls_eps,

@@ -4,6 +4,11 @@
 #include "spb_common.cuh"
 #include "spb_frame_stages.cuh"
 
+// sums that several threads add into one pixel are kept in 32.32 fixed point and added with 64-bit integer atomics:
+// independent of the order of arrival (bit-reproducible), exact up to 2^-32, rounded to float32 once
+#define SPB_AVG_FX 4294967296.0   /* 2^32 */
+__device__ __forceinline__ unsigned long long to_fx(float z) { return (unsigned long long)((double)z * SPB_AVG_FX + 0.5); }
+
 // ------------------------------------------------------------------------------------------------
 // compaction pass 1: one warp per (segment,row): number of mask pixels in the row.
 // The masks are N*H*W bytes (the largest thing the build reads: 31 MB at 640x480x100, 201 MB at 1024x768x256) and are
@@ -320,7 +325,7 @@ extern "C" int spb_dense_depths(const uint8_t* masks, const float* logd, int64_t
 template <bool SPLAT>
 __global__ void k_lift(const __grid_constant__ SpbGeom g, const float* __restrict__ k, const float* __restrict__ pose,
                        float* __restrict__ src_pts, int64_t* __restrict__ seg_ids, uint8_t* __restrict__ src_ok,
-                       int mean, unsigned long long* __restrict__ keys, float* __restrict__ sum) {
+                       int mean, unsigned long long* __restrict__ keys, unsigned long long* __restrict__ sum) {
     const int lane = threadIdx.x & 31;
     const int wglobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int wstride = gridDim.x * (blockDim.x >> 5);
@@ -361,7 +366,7 @@ __global__ void k_lift(const __grid_constant__ SpbGeom g, const float* __restric
                 if (row < 0 || row >= g.H || col < 0 || col >= g.W) continue;
                 const int idx = row * g.W + col;
                 if (mean) {
-                    atomicAdd(sum + idx, Yz);
+                    if (Yz < 2.0e9f) atomicAdd(sum + idx, to_fx(Yz));
                     atomicAdd(keys + idx, 1ull);
                 } else {
                     // last writer in point order wins == CPU scatter_ semantics
@@ -373,12 +378,12 @@ __global__ void k_lift(const __grid_constant__ SpbGeom g, const float* __restric
     }
 }
 
-__global__ void k_splat_resolve(const unsigned long long* __restrict__ keys, const float* __restrict__ sum, int mean,
-                                int HW, float* __restrict__ out) {
+__global__ void k_splat_resolve(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ sum,
+                                int mean, int HW, float* __restrict__ out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
         const unsigned long long key = keys[i];
         if (mean)   // scatter_reduce_('mean') with include_self=True: (0 + sum) / (count + 1)
-            out[i] = key ? sum[i] / (float)(key + 1ull) : 0.0f;
+            out[i] = key ? (float)((double)sum[i] * (1.0 / SPB_AVG_FX)) / (float)(key + 1ull) : 0.0f;
         else
             out[i] = key ? __uint_as_float((unsigned)(key & 0xffffffffull)) : 0.0f;
     }
@@ -400,7 +405,7 @@ extern "C" int spb_lift_points(const SpbGeom* geom, const float* k, float* src_p
 }
 
 extern "C" int spb_depth_splat(const SpbGeom* geom, const float* k, const float* pose, int mean,
-                               unsigned long long* keys, float* sum, float* out, void* stream) {
+                               unsigned long long* keys, unsigned long long* sum, float* out, void* stream) {
     if (!geom || !k || !keys || !out || geom->n_tiles < 1) return SPB_EINVAL;
     if (mean && !sum) return SPB_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
@@ -408,7 +413,7 @@ extern "C" int spb_depth_splat(const SpbGeom* geom, const float* k, const float*
     cudaError_t e = cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)HW, st);
     if (e != cudaSuccess) return (int)e;
     if (mean) {
-        e = cudaMemsetAsync(sum, 0, sizeof(float) * (size_t)HW, st);
+        e = cudaMemsetAsync(sum, 0, sizeof(unsigned long long) * (size_t)HW, st);
         if (e != cudaSuccess) return (int)e;
     }
     k_lift<true><<<lift_blocks(geom->n_tiles), 256, 0, st>>>(*geom, k, pose, nullptr, nullptr, nullptr, mean, keys, sum);
@@ -489,7 +494,6 @@ __global__ void k_depth_avg_dense(float* __restrict__ depths, int N, int HW, flo
 // Overlapping segments add into the same pixel from different warps: the sum is accumulated in 32.32 fixed point with
 // 64-bit integer atomics and the count with 32-bit ones, so the result does not depend on the order of arrival
 // (bit-reproducible, and the same on any number of GPUs); the exact sum is rounded to float32 once.
-#define SPB_AVG_FX 4294967296.0   /* 2^32 */
 __global__ void k_depth_avg_compact(const __grid_constant__ SpbGeom g, const float* __restrict__ k,
                                     const uint8_t* __restrict__ visible, unsigned long long* __restrict__ sum,
                                     uint32_t* __restrict__ cnt) {
@@ -507,7 +511,7 @@ __global__ void k_depth_avg_compact(const __grid_constant__ SpbGeom g, const flo
             const int u = (int)(w & 0xffffu), v = (int)((w >> 16) & 0x7fffu);
             const float z = expf(g.logd[p] + shift);
             if (z > 1e-6f && z < 2.0e9f) {
-                atomicAdd(sum + (size_t)v * g.W + u, (unsigned long long)((double)z * SPB_AVG_FX + 0.5));
+                atomicAdd(sum + (size_t)v * g.W + u, to_fx(z));
                 atomicAdd(cnt + (size_t)v * g.W + u, 1u);
             }
         }
@@ -552,7 +556,7 @@ extern "C" int spb_depth_avg_compact(const SpbGeom* geom, const float* k, const 
 
 // estimate_depth_diff for arbitrary points (core/ops.py:59-96): same splat as k_lift<true>, input (P,3)
 __global__ void k_splat_points(const float* __restrict__ pts, int P, const float* __restrict__ K, int H, int W,
-                               int mean, unsigned long long* __restrict__ keys, float* __restrict__ sum,
+                               int mean, unsigned long long* __restrict__ keys, unsigned long long* __restrict__ sum,
                                uint8_t* __restrict__ valid) {
     const float fx = K[0], fy = K[4], cx = K[2], cy = K[5];
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < P; q += gridDim.x * blockDim.x) {
@@ -569,7 +573,7 @@ __global__ void k_splat_points(const float* __restrict__ pts, int P, const float
         if (!ok) continue;
         const int idx = row * W + col;
         if (mean) {
-            atomicAdd(sum + idx, Z);
+            if (Z < 2.0e9f) atomicAdd(sum + idx, to_fx(Z));
             atomicAdd(keys + idx, 1ull);
         } else {
             atomicMax(keys + idx, ((unsigned long long)(q + 1) << 32) | __float_as_uint(Z));
@@ -578,7 +582,7 @@ __global__ void k_splat_points(const float* __restrict__ pts, int P, const float
 }
 
 extern "C" int spb_depth_splat_points(const float* pts, int P, const float* K, int H, int W, int mean,
-                                      unsigned long long* keys, float* sum, float* out, uint8_t* valid,
+                                      unsigned long long* keys, unsigned long long* sum, float* out, uint8_t* valid,
                                       void* stream) {
     if (!pts || P < 1 || !K || H < 1 || W < 1 || !keys || !out) return SPB_EINVAL;
     if (mean && !sum) return SPB_EINVAL;
@@ -587,7 +591,7 @@ extern "C" int spb_depth_splat_points(const float* pts, int P, const float* K, i
     cudaError_t e = cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)HW, st);
     if (e != cudaSuccess) return (int)e;
     if (mean) {
-        e = cudaMemsetAsync(sum, 0, sizeof(float) * (size_t)HW, st);
+        e = cudaMemsetAsync(sum, 0, sizeof(unsigned long long) * (size_t)HW, st);
         if (e != cudaSuccess) return (int)e;
     }
     int bx = (P + 255) / 256;

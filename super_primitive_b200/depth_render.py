@@ -23,7 +23,7 @@ def estimate_depth_kf_native(kf, kf_logdepth, pose=None, mean=False):
         dev = k_c.device
         H, W = geom.H, geom.W
         keys = torch.empty(H * W, dtype=torch.int64, device=dev)
-        acc = torch.empty(H * W, dtype=torch.float32, device=dev) if mean else None
+        acc = torch.empty(H * W, dtype=torch.int64, device=dev) if mean else None   # 32.32 fixed-point sums
         out = torch.empty((H, W), dtype=torch.float32, device=dev)
         pose_c = None if pose is None else _f32c(pose)
         nat.check(nat.lib().spb_depth_splat(geom.cref, k_c.data_ptr(), nat.ptr(pose_c), 1 if mean else 0,

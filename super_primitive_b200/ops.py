@@ -55,7 +55,7 @@ def estimate_depth_diff(points_3d, K, spatial_dim, mean=False):
         H, W = int(spatial_dim[0]), int(spatial_dim[1])
         dev = pts.device
         keys = torch.empty(H * W, dtype=torch.int64, device=dev)
-        acc = torch.empty(H * W, dtype=torch.float32, device=dev) if mean else None
+        acc = torch.empty(H * W, dtype=torch.int64, device=dev) if mean else None   # 32.32 fixed-point sums
         out = torch.empty((1, H, W), dtype=torch.float32, device=dev)
         valid = torch.empty(pts.shape[0], dtype=torch.uint8, device=dev)
         Kc = _f32c(K)
