@@ -892,27 +892,13 @@ __global__ void k_finalize_points(int ctas, int P, const float* __restrict__ wor
 // ------------------------------------------------------------------------------------------------
 // host-side launch helpers (C ABI)
 // ------------------------------------------------------------------------------------------------
-static int sm_count() {
-    // queried once (per process; every rank sees one kind of GPU)
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-            n = v;
-        else
-            return 148;
-    }
-    return n;
-}
-
 static inline int ctas_for(int n_tiles, int n_pairs, int occ) {
     // every warp streams a strided set of tiles through its own ring.  Size the grid to (nearly) a whole number of
     // waves of the kernel's occupancy (`occ` CTAs/SM): the smallest CTA count per pair that gives >= 3 waves over all
     // pairs with a last wave >= 97 % full, else the fullest within 8 waves (a 5.3-wave grid wastes a third of its last wave; 1024 pairs
     // with one CTA each would run 2.3 waves at 77 %).
     const int max_ctas = (n_tiles + SPB_WARPS - 1) / SPB_WARPS;
-    const int slots = sm_count() * occ;
+    const int slots = spb_sm_count() * occ;
     if (n_pairs < 1) n_pairs = 1;
     if ((long long)n_pairs * max_ctas <= slots) return max_ctas;
     int best = 1;
@@ -943,7 +929,7 @@ static inline cudaError_t allow_dyn_smem(K kernel) {
 
 static inline int ctas_for_points(int P) {
     int want = (P + SPB_THREADS * 4 - 1) / (SPB_THREADS * 4);
-    if (want > sm_count() * 4) want = sm_count() * 4;
+    if (want > spb_sm_count() * 4) want = spb_sm_count() * 4;
     if (want < 1) want = 1;
     return want;
 }

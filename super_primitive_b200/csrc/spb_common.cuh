@@ -16,6 +16,21 @@
 #define SPB_THREADS (SPB_WARPS * 32)
 #define SPB_PPT (SPB_TILE / 32)   // points per lane per tile
 
+// number of SMs of the current device, queried once per process (every rank sees one kind of GPU); grids of the
+// streaming kernels are capped at a multiple of it
+static inline int spb_sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+            n = v;
+        else
+            return 148;     // B200; only reached without a usable device (sizing queries on a CPU-only host)
+    }
+    return n;
+}
+
 #define SPB_CHECK_LAUNCH()                                  \
     do {                                                    \
         cudaError_t e__ = cudaGetLastError();               \

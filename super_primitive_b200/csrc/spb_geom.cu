@@ -248,7 +248,7 @@ extern "C" int spb_pack_rgba(const float* planar, int64_t img_stride, int n_img,
     if (!planar || !rgba || n_img < 1 || Hl < 1 || Wl < 1) return SPB_EINVAL;
     const int HW = Hl * Wl;
     int bx = (HW + 255) / 256;
-    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx > spb_sm_count() * 8) bx = spb_sm_count() * 8;
     k_pack_rgba<<<dim3(bx, n_img), 256, 0, (cudaStream_t)stream>>>(planar, img_stride, HW,
                                                                   reinterpret_cast<float4*>(rgba));
     SPB_CHECK_LAUNCH();
@@ -271,7 +271,7 @@ extern "C" int spb_sample_source(const SpbGeom* geom, const float* src_planar, i
                                  void* stream) {
     if (!geom || !src_planar || !out || Hl < 1 || Wl < 1 || geom->n_pad < 1) return SPB_EINVAL;
     int bx = (geom->n_pad + 255) / 256;
-    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx > spb_sm_count() * 8) bx = spb_sm_count() * 8;
     k_sample_source<<<bx, 256, 0, (cudaStream_t)stream>>>(*geom, src_planar, Hl, Wl, out);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
@@ -391,7 +391,7 @@ __global__ void k_splat_resolve(const unsigned long long* __restrict__ keys, con
 
 static inline int lift_blocks(int n_tiles) {
     int bx = (n_tiles + 7) / 8;
-    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx > spb_sm_count() * 8) bx = spb_sm_count() * 8;
     return bx < 1 ? 1 : bx;
 }
 
@@ -419,7 +419,7 @@ extern "C" int spb_depth_splat(const SpbGeom* geom, const float* k, const float*
     k_lift<true><<<lift_blocks(geom->n_tiles), 256, 0, st>>>(*geom, k, pose, nullptr, nullptr, nullptr, mean, keys, sum);
     SPB_CHECK_LAUNCH();
     int bx = (HW + 255) / 256;
-    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx > spb_sm_count() * 8) bx = spb_sm_count() * 8;
     k_splat_resolve<<<bx, 256, 0, st>>>(keys, sum, mean, HW, out);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
@@ -530,7 +530,7 @@ extern "C" int spb_depth_avg_dense(float* depths, int N, int H, int W, float* ou
     if (!depths || !out || !invalid || N < 1 || H < 1 || W < 1) return SPB_EINVAL;
     const int HW = H * W;
     int bx = (HW + 255) / 256;
-    if (bx > 148 * 16) bx = 148 * 16;
+    if (bx > spb_sm_count() * 16) bx = spb_sm_count() * 16;
     k_depth_avg_dense<<<bx, 256, 0, (cudaStream_t)stream>>>(depths, N, HW, out, invalid);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
@@ -548,7 +548,7 @@ extern "C" int spb_depth_avg_compact(const SpbGeom* geom, const float* k, const 
     k_depth_avg_compact<<<lift_blocks(geom->n_tiles), 256, 0, st>>>(*geom, k, visible, sum, cnt);
     SPB_CHECK_LAUNCH();
     int bx = (HW + 255) / 256;
-    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx > spb_sm_count() * 8) bx = spb_sm_count() * 8;
     k_depth_avg_resolve<<<bx, 256, 0, st>>>(sum, cnt, HW, out, invalid);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
@@ -595,11 +595,11 @@ extern "C" int spb_depth_splat_points(const float* pts, int P, const float* K, i
         if (e != cudaSuccess) return (int)e;
     }
     int bx = (P + 255) / 256;
-    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx > spb_sm_count() * 8) bx = spb_sm_count() * 8;
     k_splat_points<<<bx, 256, 0, st>>>(pts, P, K, H, W, mean, keys, sum, valid);
     SPB_CHECK_LAUNCH();
     int br = (HW + 255) / 256;
-    if (br > 148 * 8) br = 148 * 8;
+    if (br > spb_sm_count() * 8) br = spb_sm_count() * 8;
     k_splat_resolve<<<br, 256, 0, st>>>(keys, sum, mean, HW, out);
     SPB_CHECK_LAUNCH();
     return SPB_OK;

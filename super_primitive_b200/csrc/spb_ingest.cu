@@ -114,7 +114,7 @@ extern "C" int spb_ingest_u8(const SpbGeom* geoms, const SpbFrameJob* jobs, int 
     // grid.x sized so that all jobs together fill the 148 SMs a few times over; every kernel loops with a grid stride
     auto gx = [&](int items_per_cta, int items) {
         int want = (items + items_per_cta - 1) / items_per_cta;
-        int cap = (148 * 16 + n_jobs - 1) / n_jobs;
+        int cap = (spb_sm_count() * 16 + n_jobs - 1) / n_jobs;
         if (cap < 1) cap = 1;
         return want < cap ? want : cap;
     };
@@ -147,7 +147,7 @@ extern "C" int spb_image_tt(const uint8_t* hwc, int H, int W, float* chw, void* 
     if (!hwc || !chw || H < 1 || W < 1) return SPB_EINVAL;
     const int HW = H * W;
     int bx = (HW + 255) / 256;
-    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx > spb_sm_count() * 8) bx = spb_sm_count() * 8;
     k_image_tt<<<bx, 256, 0, (cudaStream_t)stream>>>(hwc, HW, chw);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
