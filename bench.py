@@ -684,6 +684,33 @@ def main():
         except Exception as e:      # noqa: BLE001
             mapping = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- the same batch size on SAM-like blob segments (the headline keeps round 1's overlapping strips) ----------
+    blobs = None
+    if rank == 0 and not args.no_e2e:
+        try:
+            import bench_workloads as bw
+            from super_primitive_b200.solver import AlignmentBatch
+            bb = AlignmentBatch(bw.build_pair_units(list(range(args.pairs)), WORKLOAD["H"], WORKLOAD["W"], WORKLOAD["N"],
+                                                    device, n_geoms=4, pad=4))
+            blobs = {"segments": "8x8 grid cells dilated by 4 px (rows of a segment are 88 px wide instead of 18)",
+                     "points_per_pair": bb.points_total // bb.n}
+            for name, fn, gn in (("gn", bb.gn_step, True), ("first_order", bb.adam_step, False)):
+                for _ in range(warm):
+                    fn()
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+                for a, b in evs:
+                    a.record()
+                    b.record()
+                torch.cuda.synchronize()
+                for i in range(steps):
+                    fn(evs[i])
+                torch.cuda.synchronize()
+                kms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+                blobs[name] = {"kernel_ms": kms, "algorithmic_bytes_per_launch": int(bb.algorithmic_bytes_per_iter(gn=gn))}
+            del bb
+        except Exception as e:      # noqa: BLE001
+            blobs = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- the only collective of the path: final gather of poses / seeds / cost -------------------------
     gather_ms = None
     if world > 1:
@@ -754,6 +781,11 @@ def main():
             line["dropin_single_pair"] = dropin
             line["device_loop_single_pair"] = device_loop
             line["mapping_windows"] = mapping
+        if blobs is not None:
+            for name in ("gn", "first_order"):
+                if name in blobs:
+                    blobs[name]["roofline_frac"] = blobs[name]["algorithmic_bytes_per_launch"] / (blobs[name]["kernel_ms"] * 1e-3) / 1e9 / peak
+            line["blob_segments"] = blobs
         if gather_ms is not None:
             line["final_gather_ms"] = gather_ms
         print(json.dumps(line), flush=True)
