@@ -36,15 +36,18 @@ def _f64(kf):
     return KeyFrame(c(kf.image), c(kf.K), c(kf.logdepth_perseg), c(kf.keypoints), kf.keypoint_regions, c(kf.K_img))
 
 
-def _elem_bar(got, ref32, ref64, what, tol=1e-4, flip=0.0):
+def _elem_bar(got, ref32, ref64, what, tol=1e-4, flip=0.0, floor=0.0):
     """element-wise: GPU vs float64 within max(tol, 2 x the float32 reference's own element-wise distance to float64).
     (Small entries of a gradient are sums with heavy cancellation: one sign(r) flip of a near-zero residual moves them by
     more than 1e-4 of their size in the reference's own float32 evaluation -- measured 2e-3 on the C2 batch pose gradient.)
+    `floor`: lower limit of the bar where the float32 reference's own element-wise distance is known to sit at a few
+    1e-4 (C2 shape: 2-5e-4 measured, printed below) but depends on how the host's torch splits its float32 sums over
+    threads -- the bar must not shrink below what the reference itself delivers on another host.
     `flip`: absolute change of an entry when ONE residual changes sign (2 / (3 P B) for the brightness offset, whose
     gradient is a plain sum of signs that nearly cancels); up to 16 such flips out of ~1.6 M residuals are rounding, not error."""
     got, ref32, ref64 = (np.asarray(a, np.float64) for a in (got, ref32, ref64))
     e_gpu, e_ref = elem_err(got, ref64), elem_err(ref32, ref64)
-    bar = max(tol, 2.0 * e_ref)
+    bar = max(tol, 2.0 * e_ref, floor)
     scale = np.maximum(np.abs(ref64), 1e-3 * max(np.abs(ref64).max(), 1e-30))
     ok = np.abs(got - ref64) <= np.maximum(bar * scale, 16.0 * flip)
     print(f"  {what}: GPU vs float64 {e_gpu:.2e}, float32 reference vs float64 {e_ref:.2e} (element-wise)"
@@ -83,8 +86,8 @@ def test_c2_single_target_against_oracle(c2, level):
     out = do.photomeric_cost(s.to("cuda"), t.to("cuda"), kg, pg, CFG0)
     out['residual'].mean().backward()
     assert_close(to_np(out['residual']), to_np(r64['residual']), 2e-5, f"C2 L{level} cost")
-    _elem_bar(to_np(kg.grad), to_np(k32.grad), to_np(k64.grad), f"C2 L{level} d/dk (64 entries)")
-    _elem_bar(to_np(pg.grad)[:3], to_np(p32.grad)[:3], to_np(p64.grad)[:3], f"C2 L{level} d/dpose")
+    _elem_bar(to_np(kg.grad), to_np(k32.grad), to_np(k64.grad), f"C2 L{level} d/dk (64 entries)", floor=1e-3)
+    _elem_bar(to_np(pg.grad)[:3], to_np(p32.grad)[:3], to_np(p64.grad)[:3], f"C2 L{level} d/dpose", floor=1e-3)
     assert float(to_np(pg.grad)[3].max()) == 0.0
 
 
@@ -112,8 +115,8 @@ def test_c2_batch_of_four_targets_against_oracle(c2):
     out = dob.photomeric_cost_batch(s.to("cuda"), imgs.cuda(), Ks.cuda(), kg, pg, CFG0, (asg, atg))
     out['residual'].mean().backward()
     assert_close_elem(to_np(out['residual']), to_np(r64['residual']), 2e-5, "C2 batch cost")
-    _elem_bar(to_np(kg.grad), to_np(k32.grad), to_np(k64.grad), "C2 batch d/dk")
-    _elem_bar(to_np(pg.grad)[:, :3], to_np(p32.grad)[:, :3], to_np(p64.grad)[:, :3], "C2 batch d/dposes")
+    _elem_bar(to_np(kg.grad), to_np(k32.grad), to_np(k64.grad), "C2 batch d/dk", floor=1e-3)
+    _elem_bar(to_np(pg.grad)[:, :3], to_np(p32.grad)[:, :3], to_np(p64.grad)[:, :3], "C2 batch d/dposes", floor=4e-3)
     flip = 2.0 / (3.0 * int(s.keypoint_regions.sum()) * B)
     _elem_bar(to_np(asg.grad), to_np(as32.grad), to_np(as64.grad), "C2 batch d/d aff_src", flip=flip)
     _elem_bar(to_np(atg.grad), to_np(at32.grad), to_np(at64.grad), "C2 batch d/d aff_trg", flip=flip)
@@ -141,7 +144,7 @@ def test_c2_precomputed_tracking_against_oracle(c2):
     out = do.photomeric_cost_precomputed(pre, t.to("cuda"), pg, CFG0, (a_s.cuda(), atg))
     out['residual'].mean().backward()
     assert_close(to_np(out['residual']), to_np(r64['residual']), 2e-5, "C2 tracking cost")
-    _elem_bar(to_np(pg.grad)[:3], to_np(p32.grad)[:3], to_np(p64.grad)[:3], "C2 tracking d/dpose")
+    _elem_bar(to_np(pg.grad)[:3], to_np(p32.grad)[:3], to_np(p64.grad)[:3], "C2 tracking d/dpose", floor=1e-3)
     _elem_bar(to_np(atg.grad), to_np(at32.grad), to_np(at64.grad), "C2 tracking d/d aff_trg",
               flip=2.0 / (3.0 * int(s.keypoint_regions.sum())))
 
@@ -227,10 +230,12 @@ def test_dropin_sfm_loop_first_iterations_track_the_reference_loop():
     assert float(np.abs(to_np(w32['k']) - z["k0"]).max()) > 0.03          # ~ lr * iterations: a real trajectory
     # the first 20 iterations, before rounding has been amplified: tight
     np.testing.assert_allclose(losses[:20], w64['losses'][:20], rtol=1e-4)
-    _traj_bar(losses, w32['losses'], w64['losses'], "loss trajectory (120 iterations)")
-    _traj_bar(to_np(k), to_np(w32['k']), to_np(w64['k']), "seeds after 120 iterations")
+    # measured: loss 5.5e-5, seeds 1.1e-4, increments 1.2e-4 from the float64 loop, the reference's own float32 loop
+    # 5.6e-5 / 1.0e-4 / 1.9e-4 (its value depends on how the host's torch orders float32 sums, hence the fixed 3e-4 floor)
+    _traj_bar(losses, w32['losses'], w64['losses'], "loss trajectory (120 iterations)", tol=3e-4)
+    _traj_bar(to_np(k), to_np(w32['k']), to_np(w64['k']), "seeds after 120 iterations", tol=3e-4)
     _traj_bar(to_np(deltas), np.stack([to_np(d) for d in w32['deltas']]), np.stack([to_np(d) for d in w64['deltas']]),
-              "pose increments after 120 iterations")
+              "pose increments after 120 iterations", tol=3e-4)
 
 
 def test_dropin_sfm_loop_reaches_the_reference_result():
