@@ -189,3 +189,37 @@ def test_pyramid_matches_reference_semantics():
     blur = sum(ker[i, j] * pad[:, i:i + 32, j:j + 48] for i in range(3) for j in range(3))
     assert np.allclose(pyr[1].image.numpy(), blur[:, ::2, ::2], atol=1e-6)
     assert torch.allclose(pyr[0].K_img[0, 0], kf.K[0, 0] * 0.25)
+
+
+def test_precomputed_dict_drops_its_fast_path_handle_when_edited():
+    """`unproject_kf` hands back a dict subclass carrying a private handle on the compact geometry (so that
+    `photomeric_cost_precomputed` can run the fused kernel); any edit invalidates it, and it pickles as a plain dict."""
+    import copy
+    import pickle
+    from super_primitive_b200.dense_optim import _Precomputed
+    base = {'src_pts': torch.zeros(4, 3), 'src_pixels': torch.zeros(1, 3, 4), 'src_valid_mask': torch.ones(1, 4, dtype=torch.bool),
+            'segm_ids': torch.zeros(4, dtype=torch.int64), 'spatial_size': (2, 2)}
+    for edit in (lambda d: d.__setitem__('src_pts', d['src_pts'] * 2), lambda d: d.update(extra=1),
+                 lambda d: d.pop('segm_ids'), lambda d: d.setdefault('x', 0), lambda d: d.__delitem__('segm_ids')):
+        d = _Precomputed(base)
+        d._spb = ("geom", "level", "k", d['src_pts'], d['src_pixels'])
+        assert d._spb is not None and d['spatial_size'] == (2, 2)          # reads keep the handle
+        edit(d)
+        assert d._spb is None
+    d = _Precomputed(base)
+    d._spb = ("geom", "level", "k", d['src_pts'], d['src_pixels'])
+    for clone in (pickle.loads(pickle.dumps(d)), copy.deepcopy(d)):
+        assert type(clone) is dict and set(clone) == set(base)
+    assert dict(d) == base and type(dict(d)) is dict
+
+
+def test_mode_table_matches_the_reference_split():
+    """core/cost_utils.py:4-19: channel counts the modes insist on."""
+    from super_primitive_b200.dense_optim import _mode_channels
+    _mode_channels('colour', 3)
+    _mode_channels('colour', 7)                 # 'colour' slices the first three channels of anything
+    _mode_channels('colour_norm', 6)
+    _mode_channels('colour_norm_kappa', 7)
+    for mode, c in (('colour_norm', 3), ('colour_norm', 7), ('colour_norm_kappa', 6)):
+        with pytest.raises(AssertionError):
+            _mode_channels(mode, c)
