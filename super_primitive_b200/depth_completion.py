@@ -45,3 +45,49 @@ def render_segments_avg(kf, keypoint_logdepth, visible_seg=None):
                                                   out.data_ptr(), invalid.data_ptr(), _stream()),
                   "spb_depth_avg_compact")
     return out, invalid.bool()
+
+
+def complete_batch(kfs, sparse_depths, mode='median'):
+    """The reference's per-frame `DepthCompletion.infer_depth` tail (depth_completion/segment_based_completion.py:44-54:
+    `segment_based_depth_reinit(partial_depth, kf, 'median', return_info=True)` -> `unproject_kf_to_depths` -> mask ->
+    drop the unseeded segments -> `render_depth_avg`) for a BATCH of independent frames with two host syncs for the whole
+    batch instead of two per frame: all mask compactions are queued and their point counts read back together
+    (`geometry.geometries_of`), then every frame's re-initialisation and average render are queued, and the
+    'no segment saw a depth' condition (the reference fails on `torch.median` of an empty tensor) is checked once at the end.
+
+    kfs: keyframes; sparse_depths: (H,W) tensors (0 = no measurement; like the reference, entries < 1e-6 are clamped to
+    1e-6 in place).  Returns a list of (depth (H,W), invalid (H,W) bool, k (N,), visible (N,) bool)."""
+    from .geometry import geometries_of
+    if len(kfs) != len(sparse_depths):
+        raise AssertionError("one sparse depth map per keyframe expected")
+    lib = nat.lib()
+    out = []
+    with torch.no_grad():
+        geoms = geometries_of(kfs)
+        nvis_all = torch.empty(len(kfs), dtype=torch.int32, device=geoms[0].uv.device) if geoms else None
+        for i, (kf, geom, est0) in enumerate(zip(kfs, geoms, sparse_depths)):
+            dev = geom.uv.device
+            if tuple(est0.shape) != (geom.H, geom.W):
+                raise AssertionError("estimated_depth must have the keyframe's geometry size")
+            est = est0
+            if est.dtype != torch.float32 or not est.is_contiguous() or est.device != dev:
+                est = est.to(device=dev, dtype=torch.float32).contiguous()
+            N, HW = geom.N, geom.H * geom.W
+            seg_val = torch.empty(N, dtype=torch.float32, device=dev)
+            visible = torch.empty(N, dtype=torch.uint8, device=dev)
+            k = torch.empty(N, dtype=torch.float32, device=dev)
+            nat.check(lib.spb_segment_reinit(geom.cref, est.data_ptr(), 1 if mode == 'median' else 0, seg_val.data_ptr(),
+                                             visible.data_ptr(), k.data_ptr(), nvis_all[i:i + 1].data_ptr(), _stream()),
+                      "spb_segment_reinit")
+            if est0.is_floating_point():
+                est0.masked_fill_(est0 < 1e-6, 1e-6)
+            acc = torch.empty(HW, dtype=torch.int64, device=dev)
+            cnt = torch.empty(HW, dtype=torch.int32, device=dev)
+            depth = torch.empty((geom.H, geom.W), dtype=torch.float32, device=dev)
+            invalid = torch.empty((geom.H, geom.W), dtype=torch.uint8, device=dev)
+            nat.check(lib.spb_depth_avg_compact(geom.cref, k.data_ptr(), visible.data_ptr(), acc.data_ptr(), cnt.data_ptr(),
+                                                depth.data_ptr(), invalid.data_ptr(), _stream()), "spb_depth_avg_compact")
+            out.append((depth, invalid.bool(), k, visible.bool()))
+        if geoms and int(nvis_all.min().item()) == 0:
+            raise IndexError("complete_batch: a frame has no segment with a valid depth estimate")
+    return out

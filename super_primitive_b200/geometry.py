@@ -40,6 +40,31 @@ class CompactGeometry:
     """Device-resident compacted geometry of one source keyframe."""
 
     def __init__(self, regions, logd, keypoints, K):
+        self._begin(regions, logd, keypoints, K)
+        # one host sync per keyframe: three integers size the allocations (the reference syncs on torch.where every
+        # iteration); the segment pointers stay on the device and are fetched lazily for the statistics path
+        self._finish(*(int(v) for v in self._totals.tolist()))
+
+    @classmethod
+    def build_many(cls, keyframes):
+        """Compact geometries of several keyframes with ONE host sync for all of them (a batch of independent frames,
+        e.g. VOID depth completion): the count + scan passes of every keyframe are queued first, their totals are read
+        back together, then every fill pass is queued.  `keyframes`: objects with keypoint_regions / get_logdepth() /
+        keypoints / K."""
+        pend = []
+        for kf in keyframes:
+            g = cls.__new__(cls)
+            g._begin(kf.keypoint_regions, kf.get_logdepth(), kf.keypoints, kf.K)
+            pend.append(g)
+        if not pend:
+            return []
+        totals = torch.stack([g._totals for g in pend]).tolist()          # the one sync
+        for g, (P, P_pad, T) in zip(pend, totals):
+            g._finish(int(P), int(P_pad), int(T))
+        return pend
+
+    def _begin(self, regions, logd, keypoints, K):
+        """passes 1 + 2 (row counts, scan): queued on the current stream, nothing read back"""
         if not regions.is_cuda:
             raise RuntimeError("super_primitive_b200 runs on CUDA tensors only (no CPU fallback)")
         lib = nat.lib()
@@ -64,17 +89,27 @@ class CompactGeometry:
         row_off = torch.empty(N * H, **i32)
         csr = torch.empty(3 * (N + 1) + 3, **i32)          # seg_ptr | seg_ptr_pad | seg_tile | totals, one allocation
         seg_ptr, seg_ptr_pad, seg_tile = csr[:N + 1], csr[N + 1:2 * (N + 1)], csr[2 * (N + 1):3 * (N + 1)]
-        totals = csr[3 * (N + 1):]
+        self._totals = csr[3 * (N + 1):]
         nat.check(lib.spb_compact_count(m8.data_ptr(), N, H, W, row_cnt.data_ptr(), st), "spb_compact_count")
         nat.check(lib.spb_compact_scan(row_cnt.data_ptr(), N, H, row_off.data_ptr(), seg_ptr.data_ptr(),
-                                       seg_ptr_pad.data_ptr(), seg_tile.data_ptr(), totals.data_ptr(), st),
+                                       seg_ptr_pad.data_ptr(), seg_tile.data_ptr(), self._totals.data_ptr(), st),
                   "spb_compact_scan")
-        # one host sync per keyframe: three integers size the allocations (the reference syncs on torch.where every
-        # iteration); the segment pointers stay on the device and are fetched lazily for the statistics path
-        P, P_pad, T = (int(v) for v in totals.tolist())
+        self.N, self.H, self.W = N, H, W
+        self._pending = (m8, logd_c, kps, per_seg, row_off, seg_ptr, seg_ptr_pad, seg_tile)
+        self._csr = csr
+
+    def _finish(self, P, P_pad, T):
+        """pass 3 (ordered scatter) + tile table, once the point / tile counts are known on the host"""
+        lib = nat.lib()
+        m8, logd_c, kps, per_seg, row_off, seg_ptr, seg_ptr_pad, seg_tile = self._pending
+        self._pending = None
+        N, H, W = self.N, self.H, self.W
+        dev = m8.device
+        st = _stream()
+        i32 = dict(dtype=torch.int32, device=dev)
         if P <= 0:
             raise AssertionError("keyframe has no segment pixels")
-        self.N, self.H, self.W, self.P, self.P_pad = N, H, W, P, P_pad
+        self.P, self.P_pad = P, P_pad
         self.uv = torch.zeros(P_pad, dtype=torch.int32, device=dev)      # bit pattern of uint32
         self.logd = torch.zeros(P_pad, dtype=torch.float32, device=dev)
         self.seg_lkp = torch.empty(N, dtype=torch.float32, device=dev)
@@ -88,7 +123,6 @@ class CompactGeometry:
         self.seg_tile = seg_tile
         nat.check(lib.spb_tile_table(seg_ptr.data_ptr(), seg_ptr_pad.data_ptr(), seg_tile.data_ptr(), N,
                                      self.tiles.data_ptr(), st), "spb_tile_table")
-        self._csr = csr
         self._seg_ptr_host = None
         self._pad_index = None
         self._seg_ids = None
@@ -195,6 +229,30 @@ def geometry_of(kf) -> CompactGeometry:
     while len(_GEOM_CACHE) > GEOM_CACHE_SIZE:
         _GEOM_CACHE.popitem(last=False)
     return g
+
+
+def geometries_of(kfs):
+    """`geometry_of` for a batch of keyframes: cache hits are reused, all misses are built with one host sync
+    (`CompactGeometry.build_many`)."""
+    out = [None] * len(kfs)
+    miss = []
+    for i, kf in enumerate(kfs):
+        reg, ld, kp = kf.keypoint_regions, kf.get_logdepth(), kf.keypoints
+        key = (id(reg), reg._version, id(ld), ld._version, id(kp), kp._version)
+        hit = _GEOM_CACHE.get(key)
+        if hit is not None and hit[0]() is reg and hit[1]() is ld and hit[2]() is kp:
+            out[i] = geometry_of(kf)
+        else:
+            miss.append((i, key))
+    built = CompactGeometry.build_many([kfs[i] for i, _ in miss])
+    for (i, key), g in zip(miss, built):
+        kf = kfs[i]
+        g._K_src = (weakref.ref(kf.K), kf.K._version)
+        _GEOM_CACHE[key] = (weakref.ref(kf.keypoint_regions), weakref.ref(kf.get_logdepth()), weakref.ref(kf.keypoints), g)
+        out[i] = g
+    while len(_GEOM_CACHE) > max(GEOM_CACHE_SIZE, len(kfs)):
+        _GEOM_CACHE.popitem(last=False)
+    return out
 
 
 def pack_rgba(images):

@@ -277,3 +277,33 @@ def test_edge_cases_empty_segment_many_segments_single_pixel():
     torch.set_grad_enabled(True)
     assert np.array_equal(to_np(vis), to_np(vis_ref)) and not bool(vis[13])
     assert_close(to_np(kk), to_np(kk_ref), 1e-5, "reinit with empty segment")
+
+
+def test_batched_depth_completion_equals_the_per_frame_path():
+    """`depth_completion.complete_batch` (one read-back of the point counts for all frames) against
+    `segment_based_depth_reinit` + `render_segments_avg` frame by frame: bit-identical maps, seeds and visibility."""
+    from super_primitive_b200 import depth_completion as dc, depth_init, synthetic as syn
+    from super_primitive_b200.geometry import clear_caches
+    kfs, sparse = [], []
+    for i in range(5):
+        kf = syn.make_keyframe(64 + 16 * (i % 2), 96, 7 + i, kind="rects", seed=20 + i).to("cuda")
+        g = torch.Generator().manual_seed(i)
+        H, W = kf.keypoint_regions.shape[1:]
+        d = torch.zeros(H, W)
+        idx = torch.randperm(H * W, generator=g)[:300]
+        d.view(-1)[idx] = 1.0 + torch.rand(300, generator=g)
+        kfs.append(kf)
+        sparse.append(d.cuda())
+    want = []
+    for kf, sp in zip(kfs, sparse):
+        k, vis = depth_init.segment_based_depth_reinit(sp.clone(), kf, 'median', return_info=True)
+        depth, inv = dc.render_segments_avg(kf, k, vis)
+        want.append((depth, inv, k, vis))
+    torch.set_grad_enabled(True)
+    clear_caches()
+    got = dc.complete_batch(kfs, [s.clone() for s in sparse], 'median')
+    assert len(got) == 5
+    for (d0, i0, k0, v0), (d1, i1, k1, v1) in zip(want, got):
+        assert torch.equal(d0, d1) and torch.equal(i0, i1) and torch.equal(k0, k1) and torch.equal(v0, v1)
+    with pytest.raises(IndexError):                      # a frame without any measurement: the reference fails too
+        dc.complete_batch(kfs[:2], [sparse[0].clone(), torch.zeros_like(sparse[1])], 'median')
