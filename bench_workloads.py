@@ -397,7 +397,7 @@ def run_c4(ctx):
         torch.set_grad_enabled(True)
 
     steps, warm = max(1, a.steps), max(3, a.warmup)
-    total, _ = timed_steps(ctx, step, steps, warm, kernel_events=False)
+    total_pf, _ = timed_steps(ctx, step, steps, warm, kernel_events=False)
 
     # the same frames through the batched entry point: two host syncs per 32 frames instead of two per frame
     sums_b = torch.zeros_like(sums)
@@ -479,7 +479,8 @@ def run_c4(ctx):
         peak, src = hbm_peak()
         P = geom.P
         bytes_frame = 5 * N * H * W + 8 * P + 8 * P + 8 * H * W
-        frames_s = n_units * steps / (total * 1e-3)
+        frames_s = n_units * steps / (total_b * 1e-3)              # the batch entry point is what this batch config calls
+        total = total_b
         line = line_base(ctx, "depth-completion frames/sec (640x480, 100 segments per frame)", "frames/s", frames_s, steps,
                          warm, total, f"C4 VOID depth completion: {n_units} frames in total, {N} blob segments, P={P} "
                          "mask pixels/frame, 1500 sparse depths/frame", "strong",
@@ -492,10 +493,13 @@ def run_c4(ctx):
                             "traffic": None, "peak_source": src, "kernel": "k_row_count + k_row_fill (mask compaction)",
                             "algorithmic_bytes_per_frame": int(bytes_frame),
                             "note": "whole per-frame pipeline time incl. its two host syncs per frame (point count, visible count)"}
-        line["batched"] = {"value": n_units * steps / (total_b * 1e-3), "unit": "frames/s", "frames_per_call": CH,
-                           "bit_equal_to_per_frame": batched_equal,
-                           "what": "depth_completion.complete_batch: all compactions of a chunk queued, ONE read-back of "
-                                   "their point counts, then re-initialisation + render of every frame, one check at the end"}
+        line["batched"] = {"frames_per_call": CH, "bit_equal_to_per_frame": batched_equal,
+                           "what": "`value`: depth_completion.complete_batch -- all compactions of a chunk queued, ONE "
+                                   "read-back of their point counts, then re-initialisation + render of every frame, one "
+                                   "check at the end"}
+        line["per_frame_calls"] = {"value": n_units * steps / (total_pf * 1e-3), "unit": "frames/s",
+                                   "what": "segment_based_depth_reinit + render_segments_avg frame by frame (the reference's "
+                                           "call pattern: two host syncs per frame)"}
         line["shard_check"] = chk
         line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
