@@ -111,6 +111,23 @@ int spb_compact_fill(const uint8_t* masks, const float* logd, int64_t logd_seg_s
                      const float* keypoints, int N, int H, int W, const int32_t* row_off, uint32_t* uv,
                      float* L, float* seg_lkp, int32_t* kp_rc, void* stream);
 
+/* The same build straight from the frontend's hand-over (frontend/process_frame.py:231-236, image/keyframe.py:151-173;
+ * SURVEY 8(f) rank 3): `depth` = integrated_depth (N,Hf,Wf) float32, > thr inside a segment, at the frontend's
+ * resolution.  The reference resamples it to the keyframe grid (H,W) with nearest-neighbour interpolation, thresholds it
+ * into the masks, snaps every keypoint to the nearest mask pixel (put_keypoints_back) and takes the logarithm, all on
+ * dense (N,H,W) tensors; here the compact point list is written directly.  row_map [H] / col_map [W]: source row / column
+ * of every keyframe row / column (the index maps of the nearest resampling).
+ *   spb_compact_count_depth : pass 1 (then spb_compact_scan, as for masks)
+ *   spb_compact_fill_depth  : pass 3 with L = log(depth), then the keypoint snap: seg_lkp [N], kp_rc [N][2] (row, col),
+ *                             kp_norm [N][2] = the snapped keypoints, normalised like the reference (tool/point_utils.py:31-35)
+ * Segments without any pixel must have been removed by the caller (the reference drops them). */
+int spb_compact_count_depth(const float* depth, int N, int Hf, int Wf, const int32_t* row_map, const int32_t* col_map,
+                            int H, int W, float thr, int32_t* row_cnt, void* stream);
+int spb_compact_fill_depth(const float* depth, int N, int Hf, int Wf, const int32_t* row_map, const int32_t* col_map,
+                           int H, int W, float thr, const int32_t* row_off, const int32_t* seg_ptr,
+                           const int32_t* seg_ptr_pad, const float* keypoints, uint32_t* uv, float* L, float* seg_lkp,
+                           int32_t* kp_rc, float* kp_norm, void* stream);
+
 /* planar (3,Hl,Wl) -> RGBA-interleaved [Hl][Wl][4]; n_img images, src stride in floats. */
 int spb_pack_rgba(const float* planar, int64_t img_stride, int n_img, int Hl, int Wl, float* rgba,
                   void* stream);

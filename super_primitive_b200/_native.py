@@ -73,6 +73,8 @@ _PROTOS = {
     "spb_compact_count": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "spb_compact_scan": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spb_tile_table": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "spb_compact_count_depth": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _f, _vp, _vp]),
+    "spb_compact_fill_depth": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spb_compact_fill": (_i, [_vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spb_pack_rgba": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
     "spb_sample_source": (_i, [C.POINTER(SpbGeom), _vp, _i, _i, _vp, _vp]),

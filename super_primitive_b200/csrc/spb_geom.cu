@@ -158,6 +158,125 @@ __global__ void k_row_fill(const uint8_t* __restrict__ masks, const float* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Compaction straight from the frontend's output (second half).  The frontend hands over
+// `integrated_depth` (N,Hf,Wf): per-segment depth from the normal integration, 0 outside the segment, at ITS resolution;
+// the reference resamples it to the keyframe grid with nearest-neighbour interpolation, thresholds it into the masks,
+// snaps every keypoint to the nearest mask pixel and takes the logarithm -- three dense (N,H,W) tensors
+// (frontend/process_frame.py:231-236, image/keyframe.py:151-173).  Here the same result is written directly as the
+// compact point list: the index maps of the nearest resampling (row_map[H], col_map[W], produced by the same torch
+// operator on an index ramp) select the source texel, mask = depth > thr, L = log(depth).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_row_count_depth(const float* __restrict__ depth, int Hf, int Wf, const int32_t* __restrict__ row_map,
+                                  const int32_t* __restrict__ col_map, int rows, int H, int W, float thr,
+                                  int32_t* __restrict__ row_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int b = row / H, y = row - b * H;
+    const float* src = depth + ((size_t)b * Hf + row_map[y]) * Wf;
+    int n = 0;
+    for (int x = lane; x < W; x += 32) n += (src[col_map[x]] > thr);
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) row_cnt[row] = n;
+}
+
+__global__ void k_row_fill_depth(const float* __restrict__ depth, int Hf, int Wf, const int32_t* __restrict__ row_map,
+                                 const int32_t* __restrict__ col_map, int N, int H, int W, float thr,
+                                 const int32_t* __restrict__ row_off, uint32_t* __restrict__ uv, float* __restrict__ L) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= N * H) return;
+    const int b = row / H, y = row - b * H;
+    const float* src = depth + ((size_t)b * Hf + row_map[y]) * Wf;
+    const float tiw = 2.0f * (1.0f / (float)(W - 1));
+    const float tih = 2.0f * (1.0f / (float)(H - 1));
+    const bool yok = fabsf(fmaf((float)y, tih, -1.0f)) <= 0.99f;
+    int off = row_off[row];
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        const float d = (x < W) ? src[col_map[x]] : 0.0f;
+        const bool on = (x < W) && (d > thr);
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (on) {
+            const int dst = off + __popc(bal & ((1u << lane) - 1u));
+            const bool ok = yok && (fabsf(fmaf((float)x, tiw, -1.0f)) <= 0.99f);
+            uv[dst] = (uint32_t)x | ((uint32_t)y << 16) | (ok ? 0x80000000u : 0u);
+            L[dst] = logf(d);                                  // logdepth[masks] = torch.log(logdepth[masks])
+        }
+        off += __popc(bal);
+    }
+}
+
+// put_keypoints_back (image/keyframe.py:151-173): every keypoint moves to the mask pixel nearest to its rounded pixel
+// position (Euclidean; the first pixel in (row, col) order among equals = argmin's choice).  One CTA per segment over its
+// compact points: minimum of (squared distance << 32 | point index).
+__global__ void k_snap_keypoints(const uint32_t* __restrict__ uv, const float* __restrict__ L,
+                                 const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_ptr_pad,
+                                 const float* __restrict__ keypoints, int H, int W, float* __restrict__ seg_lkp,
+                                 int32_t* __restrict__ kp_rc, float* __restrict__ kp_norm) {
+    const int b = blockIdx.x;
+    const int cnt = seg_ptr[b + 1] - seg_ptr[b], start = seg_ptr_pad[b];
+    const float hr = 0.5f * ((float)H - 1.0f), hc = 0.5f * ((float)W - 1.0f);
+    const long long r0 = (long long)rintf(hr * (keypoints[2 * b] + 1.0f));          // tool/point_utils.py:37-40
+    const long long c0 = (long long)rintf(hc * (keypoints[2 * b + 1] + 1.0f));
+    unsigned long long best = ~0ull;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint32_t w = uv[start + i];
+        const long long dr = (long long)((w >> 16) & 0x7fffu) - r0, dc = (long long)(w & 0xffffu) - c0;
+        const unsigned long long key = ((unsigned long long)(dr * dr + dc * dc) << 32) | (unsigned)i;
+        best = key < best ? key : best;
+    }
+    __shared__ unsigned long long s_best[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w2 = 1; w2 < (int)(blockDim.x >> 5); ++w2) best = s_best[w2] < best ? s_best[w2] : best;
+        const int i = (int)(best & 0xffffffffull);
+        const uint32_t w = uv[start + i];
+        const int r = (int)((w >> 16) & 0x7fffu), cc = (int)(w & 0xffffu);
+        kp_rc[2 * b] = r;
+        kp_rc[2 * b + 1] = cc;
+        seg_lkp[b] = L[start + i];
+        // normalise_coordinates (tool/point_utils.py:31-35): 2 x fl32(1 / (dims - 1)) - 1
+        kp_norm[2 * b] = __fadd_rn(__fmul_rn((float)(2 * r), __fdiv_rn(1.0f, (float)H - 1.0f)), -1.0f);
+        kp_norm[2 * b + 1] = __fadd_rn(__fmul_rn((float)(2 * cc), __fdiv_rn(1.0f, (float)W - 1.0f)), -1.0f);
+    }
+}
+
+extern "C" int spb_compact_count_depth(const float* depth, int N, int Hf, int Wf, const int32_t* row_map,
+                                       const int32_t* col_map, int H, int W, float thr, int32_t* row_cnt, void* stream) {
+    if (!depth || !row_map || !col_map || !row_cnt || N < 1 || Hf < 1 || Wf < 1 || H < 2 || W < 2 || H > 32767 || W > 65535)
+        return SPB_EINVAL;
+    const int rows = N * H;
+    k_row_count_depth<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(depth, Hf, Wf, row_map, col_map, rows, H, W, thr,
+                                                                        row_cnt);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+extern "C" int spb_compact_fill_depth(const float* depth, int N, int Hf, int Wf, const int32_t* row_map,
+                                      const int32_t* col_map, int H, int W, float thr, const int32_t* row_off,
+                                      const int32_t* seg_ptr, const int32_t* seg_ptr_pad, const float* keypoints,
+                                      uint32_t* uv, float* L, float* seg_lkp, int32_t* kp_rc, float* kp_norm,
+                                      void* stream) {
+    if (!depth || !row_map || !col_map || !row_off || !seg_ptr || !seg_ptr_pad || !keypoints || !uv || !L || !seg_lkp ||
+        !kp_rc || !kp_norm || N < 1)
+        return SPB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rows = N * H;
+    k_row_fill_depth<<<(rows + 7) / 8, 256, 0, st>>>(depth, Hf, Wf, row_map, col_map, N, H, W, thr, row_off, uv, L);
+    SPB_CHECK_LAUNCH();
+    k_snap_keypoints<<<N, 256, 0, st>>>(uv, L, seg_ptr, seg_ptr_pad, keypoints, H, W, seg_lkp, kp_rc, kp_norm);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
 // keypoint pixel (round half even) and log-depth at the keypoint, core/dense_optim.py:51-64
 __global__ void k_keypoints(const float* __restrict__ keypoints, const float* __restrict__ logd, int64_t seg_stride,
                             int N, int H, int W, float* __restrict__ seg_lkp, int32_t* __restrict__ kp_rc) {

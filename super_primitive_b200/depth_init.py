@@ -23,10 +23,10 @@ from .geometry import _stream, geometry_of
 def segment_based_depth_reinit(estimated_depth, kf, mode='mean', return_info=False):
     assert mode == 'mean' or mode == 'median'
     torch.set_grad_enabled(False)
-    device = kf.logdepth_perseg.device
+    geom = geometry_of(kf)
+    device = geom.uv.device
     if isinstance(estimated_depth, np.ndarray):
         estimated_depth = torch.from_numpy(estimated_depth).to(device)
-    geom = geometry_of(kf)
     if tuple(estimated_depth.shape) != (geom.H, geom.W):
         raise AssertionError("estimated_depth must have the keyframe's geometry size")
     est = estimated_depth

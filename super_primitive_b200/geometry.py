@@ -123,12 +123,18 @@ class CompactGeometry:
         self.seg_tile = seg_tile
         nat.check(lib.spb_tile_table(seg_ptr.data_ptr(), seg_ptr_pad.data_ptr(), seg_tile.data_ptr(), N,
                                      self.tiles.data_ptr(), st), "spb_tile_table")
+        self._finish_host_state(self._csr)
+
+    def _finish_host_state(self, csr):
+        """descriptor + caches, once every device array exists"""
+        self._csr = csr
+        self._pending = None
         self._seg_ptr_host = None
         self._pad_index = None
         self._seg_ids = None
         self.c = nat.SpbGeom(self.uv.data_ptr(), self.logd.data_ptr(), self.tiles.data_ptr(),
                              self.seg_tile.data_ptr(), self.seg_lkp.data_ptr(), self.K.data_ptr(),
-                             P, P_pad, N, T, H, W)
+                             self.P, self.P_pad, self.N, self.n_tiles, self.H, self.W)
         self.cref = C.byref(self.c)
         self._levels = OrderedDict()     # source-sample caches per (image identity)
         self._work = {}
@@ -212,6 +218,9 @@ def geometry_of(kf) -> CompactGeometry:
     level its own `K.clone()` (image/keyframe.py:125-146), and with `geo_down=False` -- every caller -- all levels share
     one geometry.  When a hit arrives with a different K tensor its values are copied into the geometry's own device
     buffer (stream-ordered, no host sync), so the three compaction passes and their one host sync run once per keyframe."""
+    own = getattr(kf, "_spb_geometry", None)        # handover.CompactKeyFrame: the geometry IS the keyframe
+    if own is not None:
+        return own
     reg, ld, kp, K = kf.keypoint_regions, kf.get_logdepth(), kf.keypoints, kf.K
     key = (id(reg), reg._version, id(ld), ld._version, id(kp), kp._version)
     hit = _GEOM_CACHE.get(key)
@@ -237,6 +246,9 @@ def geometries_of(kfs):
     out = [None] * len(kfs)
     miss = []
     for i, kf in enumerate(kfs):
+        if getattr(kf, "_spb_geometry", None) is not None:
+            out[i] = kf._spb_geometry
+            continue
         reg, ld, kp = kf.keypoint_regions, kf.get_logdepth(), kf.keypoints
         key = (id(reg), reg._version, id(ld), ld._version, id(kp), kp._version)
         hit = _GEOM_CACHE.get(key)

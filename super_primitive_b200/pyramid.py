@@ -63,6 +63,17 @@ def keyframe_pyramid(keyframe, start_level, end_level, geo_down=False, drop_norm
         depth_pyr = mask_pyr = [None] * len(image_pyr)
     intr_pyr = [level_intrinsics(keyframe.K, i) for i in range(start_level, end_level)][::-1]
     out = []
+    compact = getattr(keyframe, "_spb_geometry", None)
+    if compact is not None and not geo_down:
+        # handover.CompactKeyFrame: the levels share its compact geometry, no dense tensor is touched
+        from .handover import CompactKeyFrame
+        for img, intr, norms in zip(image_pyr, intr_pyr, normals_pyr):
+            if norms is not None and not drop_normals:
+                img = torch.cat([img, norms.to(img.dtype)], dim=0)
+            out.append(CompactKeyFrame(img, keyframe.K.clone(), compact, keyframe.keypoints, K_img=intr,
+                                       id=getattr(keyframe, "id", None)))
+        torch.set_grad_enabled(True)
+        return out
     for img, depth, mask, intr, norms in zip(image_pyr, depth_pyr, mask_pyr, intr_pyr, normals_pyr):
         if norms is not None and not drop_normals:
             img = torch.cat([img, norms.to(img.dtype)], dim=0)

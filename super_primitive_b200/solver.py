@@ -351,6 +351,8 @@ def make_problem(src_kf, trg_image, trg_K, pose, k, geom=None, aff_src=None, aff
     levels = (start_level, end_level): additionally the image pyramid of both frames, `keyframe_pyramid`'s levels
     (image/keyframe.py:77-148: 3x3 blur + decimation per level, geometry shared), coarse -> fine."""
     if geom is None:
+        geom = getattr(src_kf, "_spb_geometry", None)          # handover.CompactKeyFrame
+    if geom is None:
         geom = CompactGeometry(src_kf.keypoint_regions, src_kf.get_logdepth(), src_kf.keypoints, src_kf.K)
     out = dict(geom=geom, K_trg=trg_K, pose=pose, k=k, aff_src=aff_src, aff_trg=aff_trg, tau=tau)
     if levels is None:

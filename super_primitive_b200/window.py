@@ -114,7 +114,8 @@ class MappingWindows:
         for i, f in enumerate(frames):
             kf = f.get('kf')
             if kf is not None:
-                g = f.get('geom') or CompactGeometry(kf.keypoint_regions, kf.get_logdepth(), kf.keypoints, kf.K)
+                g = f.get('geom') or getattr(kf, "_spb_geometry", None) or \
+                    CompactGeometry(kf.keypoint_regions, kf.get_logdepth(), kf.keypoints, kf.K)
                 if int(f['k'].shape[0]) != g.N:
                     raise AssertionError("one log-depth seed per segment expected")
                 gidx[i] = len(self.geoms)

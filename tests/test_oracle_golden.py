@@ -138,3 +138,22 @@ def test_completion_render_reproduces_reference():
         avg, inv = port.completion_render(kf, t("k"), t("visible"))
     assert np.array_equal(to_np(inv), z["invalid"])
     assert_close(to_np(avg), z["avg"], 1e-6, "average render")
+
+
+def test_frontend_handover_oracle_reproduces_the_reference():
+    """oracle/frontend_handover.py against tests/golden/handover.npz: the reference's own `put_keypoints_back` inside
+    the last lines of `process_to_kf` (nearest resampling, threshold, keypoint snap, logarithm; empty segments dropped)."""
+    import os
+    from oracle import frontend_handover as port
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "handover.npz"))
+    for name in ("half", "odd", "same"):
+        H, W = (int(v) for v in z[f"{name}_size"])
+        kp, masks, logd, good = port.handover(torch.from_numpy(z[f"{name}_depth"]), torch.from_numpy(z[f"{name}_kps"]), (H, W))
+        assert np.array_equal(kp.numpy(), z[f"{name}_keypoints"])
+        assert np.array_equal(masks.numpy(), z[f"{name}_masks"])
+        assert np.array_equal(logd.numpy(), z[f"{name}_logdepth"])
+        assert np.array_equal(good.numpy(), z[f"{name}_good"])
+        # the fixture exercises what it should: dropped segments, moved keypoints
+        assert good.sum() < len(good)
+        moved = np.abs(kp.numpy() - z[f"{name}_kps"][z[f"{name}_good"]]).max(axis=1) > 1e-6
+        assert moved.any()
