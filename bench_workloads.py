@@ -531,6 +531,33 @@ def run_compaction(ctx):
                     "GBps": nbytes / (best * 1e-3) / 1e9, "level_buffers_ms": e0.elapsed_time(e1),
                     "what": "CompactGeometry(masks, log-depth, keypoints): count + scan + fill + tile table, wall clock "
                             "incl. its one host sync; level_buffers = cached source samples + tile-major stream of one level"})
+        # the same keyframe straight from the frontend's hand-over (integrated depth at twice the keyframe resolution,
+        # frontend/process_frame.py:231-236): no dense (N,H,W) mask / log-depth tensor is ever built
+        if name == "C2":
+            from super_primitive_b200.handover import geometry_from_frontend
+            dense_depth = torch.exp(kf.logdepth_perseg) * kf.keypoint_regions
+            depth_f = dense_depth.repeat_interleave(2, 1).repeat_interleave(2, 2).contiguous()      # (N, 2H, 2W)
+            ms_h = []
+            for i in range(5):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                gh, _, _ = geometry_from_frontend(depth_f, kf.keypoints, kf.K, (H, W))
+                torch.cuda.synchronize()
+                ms_h.append((time.perf_counter() - t0) * 1e3)
+            # what the reference does with the same input before the alignment path can start
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ld = torch.nn.functional.interpolate(depth_f[:, None], size=(H, W), mode='nearest')[:, 0]
+            mk = ld > 1e-7
+            ld[mk] = torch.log(ld[mk])
+            torch.cuda.synchronize()
+            out[-1]["handover"] = {"ms_per_keyframe": min(ms_h[1:]), "points_equal_dense_route": bool(gh.P == g.P),
+                                   "frontend_bytes_read": int(depth_f.numel() * 4),
+                                   "reference_dense_ops_ms": (time.perf_counter() - t0) * 1e3,
+                                   "what": "handover.geometry_from_frontend: compact geometry straight from integrated_depth "
+                                           "(N,2H,2W) incl. keypoint snap; reference_dense_ops_ms = interpolate + threshold + "
+                                           "log on the device with torch (without put_keypoints_back's Python loop)"}
+            del dense_depth, depth_f, gh, ld, mk
         del kf, g
     if ctx.rank == 0:
         peak, src = hbm_peak()
