@@ -1,0 +1,10 @@
+#!/bin/bash
+# visit r02q: ncu of the GN kernel, strided default vs CTA-contiguous runs, on the strips headline
+TAG=r02q
+OUT=gpurun_out; mkdir -p $OUT
+L=$PWD/super_primitive_b200/csrc
+timeout 300 ncu --set full --clock-control none -k regex:k_align_global -s 3 -c 1 -f -o $OUT/prof_gn_base_$TAG \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_gn_base_$TAG.log 2>&1
+SPB200_LIB=$L/libspb200_runs.so timeout 300 ncu --set full --clock-control none -k regex:k_align_global -s 3 -c 1 -f -o $OUT/prof_gn_runs_$TAG \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_gn_runs_$TAG.log 2>&1
+ls -la $OUT/*.ncu-rep
