@@ -366,6 +366,15 @@ int spb_depth_avg_dense(float* depths, int N, int H, int W, float* out, uint8_t*
 int spb_depth_avg_compact(const SpbGeom* geom, const float* k, const uint8_t* visible, unsigned long long* sum,
                           uint32_t* cnt, float* out, uint8_t* invalid, void* stream);
 
+/* Nearest-valid hole filling (depth_completion/fill_in_tools.py:5-7 `fill_depth`: scipy's
+ * distance_transform_edt(invalid, return_indices=True), then depth[indices]) of n_frames (H,W) maps: out = depth at the
+ * nearest (exact Euclidean) pixel with invalid == 0; equidistant candidates: smallest column, then smallest row (scipy's
+ * choice).  A frame with no valid pixel yields depth[H-1][0] everywhere and index (-1, 0), as scipy + numpy do.
+ * near_row: scratch [n_frames][H][W] int32; out_idx (may be NULL): [n_frames][2][H][W] int32 (row, col) like scipy's
+ * indices.  out must not alias depth.  H, W <= 32767. */
+int spb_fill_nearest(const float* depth, const uint8_t* invalid, int n_frames, int H, int W, int32_t* near_row,
+                     float* out, int32_t* out_idx, void* stream);
+
 /* One image-pyramid step (image/gaussian_pyramid.py:53-85): dst (C, ceil(H/2), ceil(W/2)) = 3x3 [1 2 1]^2/16 blur
  * with reflect padding of src (C,H,W), decimated [::2, ::2]. */
 int spb_pyr_down(const float* src, int C, int H, int W, float* dst, void* stream);

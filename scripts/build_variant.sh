@@ -6,5 +6,5 @@ NAME=$1; shift
 cd "$(dirname "$0")/../super_primitive_b200/csrc"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -ftz=true -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -shared \
-    -o libspb200_$NAME.so spb_align.cu spb_geom.cu spb_solve.cu spb_reinit.cu spb_window.cu spb_ingest.cu
+    -o libspb200_$NAME.so spb_align.cu spb_geom.cu spb_solve.cu spb_reinit.cu spb_window.cu spb_ingest.cu spb_fill.cu
 echo "built libspb200_$NAME.so ($*)"

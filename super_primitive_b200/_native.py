@@ -106,6 +106,7 @@ _PROTOS = {
     "spb_depth_splat_points": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "spb_depth_avg_dense": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "spb_depth_avg_compact": (_i, [C.POINTER(SpbGeom), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spb_fill_nearest": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "spb_pyr_down": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "spb_lift_points": (_i, [C.POINTER(SpbGeom), _vp, _vp, _vp, _vp, _vp]),
     "spb_segment_reinit": (_i, [C.POINTER(SpbGeom), _vp, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -47,7 +47,7 @@ def render_segments_avg(kf, keypoint_logdepth, visible_seg=None):
     return out, invalid.bool()
 
 
-def complete_batch(kfs, sparse_depths, mode='median'):
+def complete_batch(kfs, sparse_depths, mode='median', fill_holes=False):
     """The reference's per-frame `DepthCompletion.infer_depth` tail (depth_completion/segment_based_completion.py:44-54:
     `segment_based_depth_reinit(partial_depth, kf, 'median', return_info=True)` -> `unproject_kf_to_depths` -> mask ->
     drop the unseeded segments -> `render_depth_avg`) for a BATCH of independent frames with two host syncs for the whole
@@ -56,7 +56,9 @@ def complete_batch(kfs, sparse_depths, mode='median'):
     'no segment saw a depth' condition (the reference fails on `torch.median` of an empty tensor) is checked once at the end.
 
     kfs: keyframes; sparse_depths: (H,W) tensors (0 = no measurement; like the reference, entries < 1e-6 are clamped to
-    1e-6 in place).  Returns a list of (depth (H,W), invalid (H,W) bool, k (N,), visible (N,) bool)."""
+    1e-6 in place).  Returns a list of (depth (H,W), invalid (H,W) bool, k (N,), visible (N,) bool); with ``fill_holes``
+    every tuple carries a fifth entry, the map with its invalid pixels filled from the nearest valid one
+    (`fill_in_tools.fill_depth`, depth_completion/fill_in_tools.py:5-7)."""
     from .geometry import geometries_of
     if len(kfs) != len(sparse_depths):
         raise AssertionError("one sparse depth map per keyframe expected")
@@ -87,7 +89,11 @@ def complete_batch(kfs, sparse_depths, mode='median'):
             invalid = torch.empty((geom.H, geom.W), dtype=torch.uint8, device=dev)
             nat.check(lib.spb_depth_avg_compact(geom.cref, k.data_ptr(), visible.data_ptr(), acc.data_ptr(), cnt.data_ptr(),
                                                 depth.data_ptr(), invalid.data_ptr(), _stream()), "spb_depth_avg_compact")
-            out.append((depth, invalid.bool(), k, visible.bool()))
+            if fill_holes:
+                from .fill_in_tools import fill_depth
+                out.append((depth, invalid.bool(), k, visible.bool(), fill_depth(depth, invalid.bool())))
+            else:
+                out.append((depth, invalid.bool(), k, visible.bool()))
         if geoms and int(nvis_all.min().item()) == 0:
             raise IndexError("complete_batch: a frame has no segment with a valid depth estimate")
     return out

@@ -157,3 +157,31 @@ def test_frontend_handover_oracle_reproduces_the_reference():
         assert good.sum() < len(good)
         moved = np.abs(kp.numpy() - z[f"{name}_kps"][z[f"{name}_good"]]).max(axis=1) > 1e-6
         assert moved.any()
+
+
+def test_fill_depth_oracle_reproduces_the_reference():
+    """oracle/fill_oracle.py against tests/golden/fill_depth.npz: the reference's own `fill_depth`
+    (depth_completion/fill_in_tools.py:5-7, scipy's Euclidean feature transform underneath), indices and filled maps bit
+    for bit -- including scipy's choice among equidistant pixels and its answer for a map with no valid pixel."""
+    import hashlib
+    import os
+    from oracle import fill_oracle as port
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fill_depth.npz"))
+    names = sorted(k[:-len("_invalid")] for k in z.files if k.endswith("_invalid"))
+    assert {"lattice", "all_invalid", "one_valid", "all_valid"} <= set(names)
+    ties = 0
+    for name in names:
+        inv, depth = z[f"{name}_invalid"], z[f"{name}_depth"]
+        ind = port.nearest_valid_indices(inv)
+        assert np.array_equal(ind, z[f"{name}_indices"]), name
+        assert np.array_equal(port.fill_depth(depth, inv), z[f"{name}_filled"]), name
+        if name == "lattice":                               # the fixture does exercise ties
+            vr, vc = np.nonzero(~inv)
+            for r, c in ((2, 2), (2, 6), (6, 2)):
+                d2 = (vr - r) ** 2 + (vc - c) ** 2
+                ties += int((d2 == d2.min()).sum() > 1)
+    assert ties == 3
+    H, W = (int(v) for v in z["vga_shape"])
+    inv = np.unpackbits(z["vga_invalid_bits"])[:H * W].reshape(H, W).astype(bool)
+    ind = port.nearest_valid_indices(inv)
+    assert hashlib.sha256(np.ascontiguousarray(ind).tobytes()).digest() == z["vga_indices_sha256"].tobytes()
