@@ -432,49 +432,51 @@ def run_c4(ctx):
              "render_ms": ev[2].elapsed_time(ev[3])}
     # nearest-valid hole filling of the completed maps (fill_in_tools.fill_depth, the exact second stage of the
     # reference's evaluation-side fill): one frame, and a chunk of frames in one call
-    from super_primitive_b200 import fill_in_tools as fit
-    res = dc.complete_batch([kf for kf, _ in frames[:CH]], [sp.clone() for _, sp in frames[:CH]], 'median')
-    d_stack = torch.stack([r[0] for r in res])
-    i_stack = torch.stack([r[1] for r in res])
-    # the synthetic segments cover the whole frame; holes like a real completion's are cut in: an unreached border,
-    # 24 rectangles of up to 1/8 of each side, 2 % isolated pixels (seeded per frame)
-    for f in range(i_stack.shape[0]):
-        gen = torch.Generator().manual_seed(1000 + f)
-        hole = torch.rand((H, W), generator=gen) < 0.02
-        hole[:, :9] = True
-        for _ in range(24):
-            r0, c0 = int(torch.randint(0, H, (1,), generator=gen)), int(torch.randint(0, W, (1,), generator=gen))
-            hole[r0:r0 + int(torch.randint(1, H // 8, (1,), generator=gen)), c0:c0 + int(torch.randint(1, W // 8, (1,), generator=gen))] = True
-        i_stack[f] |= hole.to(ctx.device)
-    fill = {"holes_frac": float(i_stack.float().mean().item())}
-    for name, (dd, ii) in (("one_frame_ms", (d_stack[:1], i_stack[:1])), ("chunk_ms", (d_stack, i_stack))):
-        for _ in range(3):
-            fit.fill_depth_batch(dd, ii)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            fit.fill_depth_batch(dd, ii)
-        e1.record()
-        torch.cuda.synchronize()
-        fill[name] = e0.elapsed_time(e1) / 10
-    fill["frames_in_chunk"] = int(d_stack.shape[0])
-    fill["frames_per_s"] = d_stack.shape[0] / (fill["chunk_ms"] * 1e-3)
-    fill["what"] = ("fill_in_tools.fill_depth_batch: exact Euclidean nearest-valid fill (scipy's tie-breaking), device "
-                    "events around the call, completed maps resident; NOT part of `value`")
-    if ctx.rank == 0 and ctx.world == 1 and not a.no_cpu_baseline:
-        try:        # the reference's own two lines (depth_completion/fill_in_tools.py:5-7) on the host
-            from scipy import ndimage as nd
-            d_np, i_np = d_stack[0].cpu().numpy(), i_stack[0].cpu().numpy()
-            nd.distance_transform_edt(i_np, return_distances=False, return_indices=True)
-            t0 = time.perf_counter()
-            for _ in range(5):
-                ind = nd.distance_transform_edt(i_np, return_distances=False, return_indices=True)
-                ref_filled = d_np[tuple(ind)]
-            fill["cpu_scipy_ms_one_frame"] = (time.perf_counter() - t0) / 5 * 1e3
-            fill["equals_scipy"] = bool(np.array_equal(fit.fill_depth_batch(d_stack[:1], i_stack[:1])[0].cpu().numpy(), ref_filled))
-        except ImportError:
-            fill["cpu_scipy_ms_one_frame"] = None
-    del res, d_stack, i_stack
+    fill = None
+    if frames:
+        from super_primitive_b200 import fill_in_tools as fit
+        res = dc.complete_batch([kf for kf, _ in frames[:CH]], [sp.clone() for _, sp in frames[:CH]], 'median')
+        d_stack = torch.stack([r[0] for r in res])
+        i_stack = torch.stack([r[1] for r in res])
+        # the synthetic segments cover the whole frame; holes like a real completion's are cut in: an unreached border,
+        # 24 rectangles of up to 1/8 of each side, 2 % isolated pixels (seeded per frame)
+        for f in range(i_stack.shape[0]):
+            gen = torch.Generator().manual_seed(1000 + f)
+            hole = torch.rand((H, W), generator=gen) < 0.02
+            hole[:, :9] = True
+            for _ in range(24):
+                r0, c0 = int(torch.randint(0, H, (1,), generator=gen)), int(torch.randint(0, W, (1,), generator=gen))
+                hole[r0:r0 + int(torch.randint(1, H // 8, (1,), generator=gen)), c0:c0 + int(torch.randint(1, W // 8, (1,), generator=gen))] = True
+            i_stack[f] |= hole.to(ctx.device)
+        fill = {"holes_frac": float(i_stack.float().mean().item())}
+        for name, (dd, ii) in (("one_frame_ms", (d_stack[:1], i_stack[:1])), ("chunk_ms", (d_stack, i_stack))):
+            for _ in range(3):
+                fit.fill_depth_batch(dd, ii)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fit.fill_depth_batch(dd, ii)
+            e1.record()
+            torch.cuda.synchronize()
+            fill[name] = e0.elapsed_time(e1) / 10
+        fill["frames_in_chunk"] = int(d_stack.shape[0])
+        fill["frames_per_s"] = d_stack.shape[0] / (fill["chunk_ms"] * 1e-3)
+        fill["what"] = ("fill_in_tools.fill_depth_batch: exact Euclidean nearest-valid fill (scipy's tie-breaking), device "
+                        "events around the call, completed maps resident; NOT part of `value`")
+        if ctx.rank == 0 and ctx.world == 1 and not a.no_cpu_baseline:
+            try:        # the reference's own two lines (depth_completion/fill_in_tools.py:5-7) on the host
+                from scipy import ndimage as nd
+                d_np, i_np = d_stack[0].cpu().numpy(), i_stack[0].cpu().numpy()
+                nd.distance_transform_edt(i_np, return_distances=False, return_indices=True)
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    ind = nd.distance_transform_edt(i_np, return_distances=False, return_indices=True)
+                    ref_filled = d_np[tuple(ind)]
+                fill["cpu_scipy_ms_one_frame"] = (time.perf_counter() - t0) / 5 * 1e3
+                fill["equals_scipy"] = bool(np.array_equal(fit.fill_depth_batch(d_stack[:1], i_stack[:1])[0].cpu().numpy(), ref_filled))
+            except ImportError:
+                fill["cpu_scipy_ms_one_frame"] = None
+        del res, d_stack, i_stack
     # gather of the per-frame checksums (the completed maps stay where they were computed)
     if ctx.world > 1:
         pad = torch.full(((n_units + ctx.world - 1) // ctx.world, 2), float('nan'), dtype=torch.float64, device=ctx.device)
