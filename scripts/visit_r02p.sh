@@ -1,5 +1,6 @@
 #!/bin/bash
 # visit r02p: CTA-contiguous tile chunks with per-run (lazy) segment flush vs the strided default
+# (experiment: the variant libraries need profiles/r02p_cta_runs.patch applied -- `git apply profiles/r02p_cta_runs.patch` -- and scripts/build_variant.sh; the default tree does not contain the switch)
 TAG=r02p
 OUT=gpurun_out; mkdir -p $OUT
 B="--no-cpu-baseline --steps 30 --warmup 5"

@@ -1,5 +1,6 @@
 #!/bin/bash
 # visit r02q: ncu of the GN kernel, strided default vs CTA-contiguous runs, on the strips headline
+# (experiment: the variant libraries need profiles/r02p_cta_runs.patch applied -- `git apply profiles/r02p_cta_runs.patch` -- and scripts/build_variant.sh; the default tree does not contain the switch)
 TAG=r02q
 OUT=gpurun_out; mkdir -p $OUT
 L=$PWD/super_primitive_b200/csrc

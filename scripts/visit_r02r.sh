@@ -1,5 +1,6 @@
 #!/bin/bash
 # visit r02r: CTA-contiguous runs with bounded chunks (more CTAs per pair -> fewer pairs in flight -> smaller L2 working set)
+# (experiment: the variant libraries need profiles/r02p_cta_runs.patch applied -- `git apply profiles/r02p_cta_runs.patch` -- and scripts/build_variant.sh; the default tree does not contain the switch)
 TAG=r02r
 OUT=gpurun_out; mkdir -p $OUT
 B="--no-cpu-baseline --steps 30 --warmup 5"

@@ -1,5 +1,6 @@
 #!/bin/bash
 # visit r02u: projected target footprint of the next tile staged in shared memory by bulk copies (SPB_BOX), taps by LDS.128
+# (experiment: the variant libraries need profiles/r02u_footprint_box.patch applied -- `git apply profiles/r02u_footprint_box.patch` -- and scripts/build_variant.sh; the default tree does not contain the switch)
 TAG=r02u
 OUT=gpurun_out; mkdir -p $OUT
 B="--no-cpu-baseline --steps 30 --warmup 5"

@@ -1,5 +1,6 @@
 #!/bin/bash
 # visit r02v: CTA-level producer/consumer pipeline with the round's projected target footprint staged in shared memory (SPB_BOXCTA)
+# (experiment: the variant libraries need profiles/r02x_boxcta.patch applied -- `git apply profiles/r02x_boxcta.patch` -- and scripts/build_variant.sh; the default tree does not contain the switch)
 TAG=r02v
 OUT=gpurun_out; mkdir -p $OUT
 B="--no-cpu-baseline --steps 30 --warmup 5"

@@ -1,5 +1,6 @@
 #!/bin/bash
 # visit r02w: SPB_BOXCTA with the producer's box computation moved ahead of its stage wait; ncu with source
+# (experiment: the variant libraries need profiles/r02x_boxcta.patch applied -- `git apply profiles/r02x_boxcta.patch` -- and scripts/build_variant.sh; the default tree does not contain the switch)
 TAG=r02w
 OUT=gpurun_out; mkdir -p $OUT
 B="--no-cpu-baseline --no-e2e --steps 30 --warmup 5"

@@ -1,5 +1,6 @@
 #!/bin/bash
 # visit r02x: SPB_BOXCTA decomposition: A = pipeline without boxes, B = boxes staged but unused, D/E = 4 consumer warps per CTA
+# (experiment: the variant libraries need profiles/r02x_boxcta.patch applied -- `git apply profiles/r02x_boxcta.patch` -- and scripts/build_variant.sh; the default tree does not contain the switch)
 TAG=r02x
 OUT=gpurun_out; mkdir -p $OUT
 B="--no-cpu-baseline --no-e2e --steps 30 --warmup 5"
