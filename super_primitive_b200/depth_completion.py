@@ -24,7 +24,7 @@ def render_depth_avg(depths):
     invalid = torch.empty((H, W), dtype=torch.uint8, device=depths.device)
     nat.check(nat.lib().spb_depth_avg_dense(depths.data_ptr(), N, H, W, out.data_ptr(), invalid.data_ptr(), _stream()),
               "spb_depth_avg_dense")
-    return out, invalid.bool()
+    return out, invalid.view(torch.bool)
 
 
 def render_segments_avg(kf, keypoint_logdepth, visible_seg=None):
@@ -44,7 +44,7 @@ def render_segments_avg(kf, keypoint_logdepth, visible_seg=None):
         nat.check(nat.lib().spb_depth_avg_compact(geom.cref, k_c.data_ptr(), nat.ptr(vis), acc.data_ptr(), cnt.data_ptr(),
                                                   out.data_ptr(), invalid.data_ptr(), _stream()),
                   "spb_depth_avg_compact")
-    return out, invalid.bool()
+    return out, invalid.view(torch.bool)
 
 
 def complete_batch(kfs, sparse_depths, mode='median', fill_holes=False):
@@ -82,7 +82,7 @@ def complete_batch(kfs, sparse_depths, mode='median', fill_holes=False):
                                              visible.data_ptr(), k.data_ptr(), nvis_all[i:i + 1].data_ptr(), _stream()),
                       "spb_segment_reinit")
             if est0.is_floating_point():
-                est0.masked_fill_(est0 < 1e-6, 1e-6)
+                est0.clamp_(min=1e-6)                      # = masked_fill_(est0 < 1e-6, 1e-6): NaN stays NaN
             acc = torch.empty(HW, dtype=torch.int64, device=dev)
             cnt = torch.empty(HW, dtype=torch.int32, device=dev)
             depth = torch.empty((geom.H, geom.W), dtype=torch.float32, device=dev)
@@ -91,9 +91,9 @@ def complete_batch(kfs, sparse_depths, mode='median', fill_holes=False):
                                                 depth.data_ptr(), invalid.data_ptr(), _stream()), "spb_depth_avg_compact")
             if fill_holes:
                 from .fill_in_tools import fill_depth
-                out.append((depth, invalid.bool(), k, visible.bool(), fill_depth(depth, invalid.bool())))
+                out.append((depth, invalid.view(torch.bool), k, visible.view(torch.bool), fill_depth(depth, invalid.view(torch.bool))))
             else:
-                out.append((depth, invalid.bool(), k, visible.bool()))
+                out.append((depth, invalid.view(torch.bool), k, visible.view(torch.bool)))
         if geoms and int(nvis_all.min().item()) == 0:
             raise IndexError("complete_batch: a frame has no segment with a valid depth estimate")
     return out

@@ -42,11 +42,11 @@ def segment_based_depth_reinit(estimated_depth, kf, mode='mean', return_info=Fal
                                            _stream()), "spb_segment_reinit")
     # reference semantics: estimated_depth[estimated_depth < eps] = eps (in place, after the read above)
     if estimated_depth.is_floating_point():
-        estimated_depth.masked_fill_(estimated_depth < 1e-6, 1e-6)
+        estimated_depth.clamp_(min=1e-6)             # = masked_fill_(est < 1e-6, 1e-6): NaN stays NaN
     if int(nvis.item()) == 0:
         # torch.median of an empty tensor: the reference fails here too
         raise IndexError("segment_based_depth_reinit: no segment has a valid depth estimate")
     torch.set_grad_enabled(False)
     if return_info:
-        return out, visible.bool()
+        return out, visible.view(torch.bool)
     return out

@@ -110,8 +110,9 @@ class CompactGeometry:
         if P <= 0:
             raise AssertionError("keyframe has no segment pixels")
         self.P, self.P_pad = P, P_pad
-        self.uv = torch.zeros(P_pad, dtype=torch.int32, device=dev)      # bit pattern of uint32
-        self.logd = torch.zeros(P_pad, dtype=torch.float32, device=dev)
+        both = torch.zeros(2 * P_pad, dtype=torch.int32, device=dev)     # one allocation + one memset for uv | logd
+        self.uv = both[:P_pad]                                           # bit pattern of uint32
+        self.logd = both[P_pad:].view(torch.float32)
         self.seg_lkp = torch.empty(N, dtype=torch.float32, device=dev)
         self.kp_rc = torch.empty((N, 2), **i32)
         nat.check(lib.spb_compact_fill(m8.data_ptr(), logd_c.data_ptr(), H * W if per_seg else 0, kps.data_ptr(),
